@@ -1,0 +1,166 @@
+/* saturn_b200.h — C ABI of the B200-native SPASE solver hot path.
+ *
+ * This is the drop-in boundary for the ONE path of knagrecha/saturn that this
+ * repository accelerates: `saturn.solver.solve()` (reference
+ * saturn/solver/milp.py:23-445), whose arithmetic the reference delegates to a
+ * third-party MILP binary (PuLP -> Gurobi/CBC, milp.py:321-327).  The library
+ * replaces that solver call with a parallel search over list-schedule
+ * candidates evaluated by hand-written sm_100a CUDA kernels.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / Python types.
+ *   - every function returns 0 on success, a negative sb_status on failure;
+ *     sb_last_error() returns a thread-local human-readable message.
+ *   - the caller allocates every buffer; the library never frees caller memory.
+ *   - "device pointer" = memory on the handle's CUDA device (e.g.
+ *     torch.Tensor.data_ptr()).  Functions ending in _host take host pointers
+ *     and perform the copies themselves.
+ *   - one handle is single-threaded; separate handles are independent.
+ *   - no CPU fallback exists: without a CUDA device sb_create fails with
+ *     SB_ERR_CUDA.
+ *
+ * Encodings (shared with the oracle, oracle/ref_eval.py)
+ *   T[J][S][G]   fp32, row-major: runtime in seconds of job j under strategy s
+ *                on gcount[g] GPUs — the profiled table the reference stores in
+ *                Task.strategies (saturn/core/representations/Task.py:118,
+ *                produced by saturn/trial_runner/PerformanceEvaluator.py:96-115).
+ *   opt[b][j]    uint8: (s << 3) | (k - 1), k = GPU count of job j's option.
+ *   prio[b][i]   uint8 (J <= 256) or uint16: job scheduled i-th; each row is a
+ *                permutation of 0..J-1.
+ *   rows of opt / prio are `row_stride` ELEMENTS apart (>= J).  When the byte
+ *   stride is a multiple of 16 and the base pointer is 16-byte aligned the rows
+ *   are fetched with TMA bulk copies, otherwise with plain loads.
+ *
+ * Evaluation rule (one node, 8 GPU slots; reference milp.py:62,139-149,209-319)
+ *   ready[0..8) = 0
+ *   for i in 0..J-1: j = prio[i]; k = (opt[j] & 7) + 1; rt = T(j, opt[j])
+ *       sel   = k slots with smallest (ready, slot)      (ties -> lowest slot)
+ *       start = max(ready[sel])
+ *       ready[sel] = start + (integer_starts ? ceil(rt) : rt)
+ *   makespan = max_j (start_j + rt_j)
+ */
+#ifndef SATURN_B200_H
+#define SATURN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+#define SB_NSLOT 8          /* GPUs per node, reference milp.py:62 */
+#define SB_MAX_STRATEGIES 32 /* 5 strategy bits in an opt byte */
+
+typedef enum sb_status {
+  SB_OK = 0,
+  SB_ERR_ARG = -1,       /* bad argument */
+  SB_ERR_CUDA = -2,      /* CUDA runtime / driver error, no device */
+  SB_ERR_STATE = -3,     /* call out of order (e.g. eval before set_table) */
+  SB_ERR_UNSUPPORTED = -4,
+  SB_ERR_NOMEM = -5
+} sb_status;
+
+/* flags for sb_eval* / sb_search */
+#define SB_FLAG_INTEGER_STARTS 1u /* MILP start variables are Integer, milp.py:142-143 */
+#define SB_FLAG_REDUCED 2u        /* opt bytes carry s = 0; the min-over-strategies table is used
+                                     (PerformanceEvaluator.py:101-115) */
+
+typedef struct sb_handle sb_handle;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int sb_abi_version(void);
+const char* sb_last_error(void);
+/* device: CUDA ordinal.  stream: the cudaStream_t every call on this handle is queued on (NULL = the
+ * context's default stream, which is what PyTorch uses unless told otherwise).  Work is ordered
+ * with the caller's other work on that stream; nothing synchronises unless documented. */
+int sb_create(int device, void* stream, sb_handle** out);
+int sb_destroy(sb_handle* h);
+/* blocks until everything queued on the handle's stream is done */
+int sb_sync(sb_handle* h);
+
+/* ---- the table (replaces milp.py:77-81 building gpu_time_tuples) --------------------------
+ * T: host or device pointer, fp32 [J][S][G]; gcount: host pointer, uint8 [G], values 1..8.
+ * nodes must be 1 (multi-node gangs are confined to one node, milp.py:117-137; N > 1 is
+ * SB_ERR_UNSUPPORTED in this version).  Builds on the device: the canonical table
+ * tab[J][S][8] (column k-1, +inf where no option), and the min-over-strategies table
+ * tmin[J][8] with argS[J][8] (first minimum wins, PerformanceEvaluator.py:105-110). */
+int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int S, int G, int nodes);
+/* Runtime threshold at and above which a table cell counts as one of the profiler's sentinels
+ * (1e6 "not profiled", 1e8 "failed", PerformanceEvaluator.py:99,106) and is never PROPOSED by the
+ * search (it is still evaluated like any number if a caller's candidate selects it).  Default 1e6;
+ * pass +inf to treat every finite cell as usable.  Takes effect at the next sb_set_table. */
+int sb_set_sentinel(sb_handle* h, float threshold);
+/* copy the reduced table back (host pointers, either may be NULL): tmin fp32 [J][8], args u8 [J][8] */
+int sb_get_reduced(sb_handle* h, float* tmin, uint8_t* args);
+
+/* ---- the measured kernel: makespan of B candidates ----------------------------------------
+ * opt, prio, makespan_out: device pointers.  prio element width is 1 byte if J <= 256 else 2.
+ * best_key (device, nullable): a uint64 the kernel atomically MINs with
+ * (float_bits(makespan) << 32) | (id_base + b), i.e. an arg-min over everything folded in. */
+int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
+            unsigned flags, float* makespan_out, uint64_t* best_key, uint32_t id_base);
+
+/* which kernel the last sb_eval / sb_eval_host on this handle used:
+ * 2 = tile kernel with TMA bulk row copies, 1 = tile kernel with plain row loads,
+ * 0 = generic kernel (rows read from global memory; J too large for shared-memory tiles) */
+int sb_last_eval_path(sb_handle* h);
+
+/* check B candidates (device pointers): every prio row is a permutation of 0..J-1 and every opt
+ * byte names an existing table cell.  sb_eval does not validate; out-of-range bytes are undefined
+ * behaviour there.  bad_rows (host) receives the number of offending rows.  Synchronous. */
+int sb_validate(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
+                unsigned flags, int64_t* bad_rows);
+
+/* same through HOST buffers: chunked H2D copies, kernel, D2H of the makespans, pipelined on
+ * two internal streams; returns when makespan_out (host) is complete. */
+int sb_eval_host(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
+                 unsigned flags, float* makespan_out);
+
+/* ---- full plan of B candidates (slot-exact; used for decode and for parity tests) ---------
+ * start_out fp32 [B][J] and slotmask_out u32 [B][J] are indexed by JOB; bit g of the mask =
+ * GPU slot g.  Device pointers; start_out / slotmask_out may be NULL. */
+int sb_eval_full(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
+                 unsigned flags, float* makespan_out, float* start_out, uint32_t* slotmask_out);
+
+/* decode ONE candidate given in host memory into host arrays (all [J]; any may be NULL):
+ * start, slot mask, strategy index s (for SB_FLAG_REDUCED the arg-min strategy of the cell),
+ * gpu count k.  makespan (nullable) receives the candidate's makespan. */
+int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags, float* start,
+              uint32_t* slotmask, uint8_t* strategy, uint8_t* gpus, float* makespan);
+
+/* ---- search (replaces prob.solve(), milp.py:321-327) ---------------------------------------
+ * A population of `chains` candidates lives on the device.  sb_search_init seeds it (random
+ * valid options + random / LPT-like priorities, optionally chain 0 from a caller-supplied
+ * warm-start candidate = the `presolved` plan of milp.py:35,103-104,151-155,197-202).
+ * sb_search_round runs `rounds` Metropolis rounds: mutate -> evaluate (the sb_eval kernel) ->
+ * accept, all on the device, and updates the best key.  The caller may exchange
+ * best keys between GPUs (one MIN all-reduce of a uint64 per round) through
+ * sb_search_best_key_ptr, and re-seed from a foreign elite with sb_search_inject. */
+typedef struct sb_search_params {
+  uint64_t seed;        /* RNG stream; candidate ids are global so ranks differ by chain_base */
+  int64_t chains;       /* candidates in this GPU's population */
+  uint64_t chain_base;  /* global id of chain 0 (rank * chains) */
+  unsigned flags;       /* SB_FLAG_* */
+  float t_start;        /* initial temperature as a fraction of the incumbent makespan */
+  float t_end;          /* final temperature fraction */
+  int total_rounds;     /* cooling horizon */
+} sb_search_params;
+
+int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_opt /*host, nullable*/,
+                   const void* warm_prio /*host, nullable*/);
+int sb_search_round(sb_handle* h, int rounds);
+/* device pointer to the uint64 best key ((makespan bits << 32) | global chain id) */
+int sb_search_best_key_ptr(sb_handle* h, uint64_t** key_dev);
+/* copy the best candidate found so far to host buffers: opt u8 [J], prio u8/u16 [J] */
+int sb_search_best(sb_handle* h, uint8_t* opt, void* prio, float* makespan, uint64_t* key);
+/* overwrite the worst `copies` chains with the given candidate (host buffers) */
+int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int copies);
+/* candidates evaluated so far by this handle's searches */
+int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATURN_B200_H */

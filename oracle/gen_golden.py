@@ -1,0 +1,167 @@
+"""Generate golden fixtures by running the UNMODIFIED reference solver.
+
+ORACLE INFRASTRUCTURE.  Runs only in the build container (needs /root/reference);
+the GPU box never executes this — it consumes the committed JSON under
+tests/golden/.
+
+    python oracle/gen_golden.py            # writes tests/golden/milp_cases.json
+
+What it does: puts oracle/shims (pulp -> scipy HiGHS, ray -> 1 node x 8 GPUs)
+and /root/reference on sys.path, imports the reference's `saturn.solver`, and
+calls `solve()` + `convert_into_comprehensible()` on small duck-typed tasks
+built from the reference's own `Strategy` class.  Two variants per case:
+
+  as_shipped : milp.py byte-for-byte (M = 1e10, milp.py:163).  Under HiGHS'
+               1e-6 integrality tolerance this big-M leaks and
+               may return overlapping schedules — recorded, with the overlap
+               count, as documentation of the hazard.
+  tight_m    : the same source with the single literal `M = 1e10` replaced at
+               load time by a sound horizon (sum of ceil(max runtime) + 1); the
+               file on disk is untouched.  This is the MILP the oracle is
+               pinned against.
+"""
+import importlib
+import json
+import math
+import os
+import random
+import sys
+import time
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def _load_reference():
+    for m in [m for m in sys.modules if m == "saturn" or m.startswith("saturn.")]:
+        del sys.modules[m]
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != os.path.dirname(HERE)]
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    import saturn.solver.milp as milp  # noqa: the reference, unmodified
+    assert milp.__file__.startswith(REF), milp.__file__
+    src = open(milp.__file__).read()
+    assert src.count("M = 1e10") == 1
+    tight_src = src.replace(
+        "M = 1e10",
+        "M = float(sum(__import__('math').ceil(max(rt for (_g, rt) in tup)) for tup in gpu_time_tuples) + 1)")
+    tight = types.ModuleType("saturn_solver_milp_tightM")
+    tight.__file__ = milp.__file__ + " [M substituted at load time]"
+    exec(compile(tight_src, tight.__file__, "exec"), tight.__dict__)
+    from saturn.core.representations import Strategy
+    import pulp
+    return milp, tight, Strategy, pulp
+
+
+class DuckTask:
+    """What solve()/convert_into_comprehensible() touch on a Task (milp.py:77-81, 481-486)."""
+
+    def __init__(self, name, strategies):
+        self.name = name
+        self.strategies = strategies
+        self.selected_strategy = None
+
+    def select_strategy(self, s):
+        self.selected_strategy = s
+
+
+def probe_tuples(J, options, seed):
+    """SURVEY §8c known-answer generator: base ~ U(500,4000), T = base / g**0.8."""
+    random.seed(seed)
+    out = []
+    for _ in range(J):
+        base = random.uniform(500, 4000)
+        out.append([(g, base / g ** 0.8) for g in options])
+    return out
+
+
+def hetero_tuples(J, seed):
+    """Per-task option lists of different lengths/orders (dict-insertion order matters)."""
+    rnd = random.Random(seed)
+    out = []
+    for _ in range(J):
+        base = rnd.uniform(200, 2000)
+        opts = rnd.sample([1, 2, 3, 4, 6, 8], rnd.randint(1, 3))
+        out.append([(g, base * rnd.uniform(1.0, 1.3) / g ** rnd.uniform(0.5, 0.95)) for g in opts])
+    return out
+
+
+def run_case(mod, Strategy, pulp, name, tuples, timeout):
+    tasks = []
+    for t, tup in enumerate(tuples):
+        strategies = {}
+        for (g, rt) in tup:
+            strategies[g] = Strategy("exec%d" % g, g, {}, rt)
+        tasks.append(DuckTask("t%d" % t, strategies))
+    t0 = time.time()
+    sta, tga, bss, bna, boa, saved = mod.solve(tasks, None, gurobi=False, threads=1, interval=1000,
+                                               timeout=timeout)
+    wall = time.time() - t0
+    info = dict(pulp.LpProblem.last_info)
+    rec = {"name": name, "gpu_time_tuples": [[list(x) for x in tup] for tup in tuples],
+           "solver_wall_s": wall, "highs": info, "returned_makespan": saved}
+    if sta is None or any(v is None for n in sta for g in n for v in g):
+        rec["incumbent"] = False
+        return rec
+    rec["incumbent"] = True
+    rec.update({"sta": sta, "tga": tga, "bss": bss, "bna": bna, "boa": boa})
+    npt, tdd, start = mod.convert_into_comprehensible(tasks, bss, boa, tga, bna, sta)
+    idx = {t: i for i, t in enumerate(tasks)}
+    rec["decoded"] = {
+        "node_per_task": [int(npt[t]) for t in tasks],
+        "deps": [sorted(idx[d] for d in tdd[t]) for t in tasks],
+        "start": [float(s) for s in start],
+        "selected_gpus": [int(t.selected_strategy.gpu_apportionment) for t in tasks],
+    }
+    rec["makespan"] = max(float(s) + t.selected_strategy.runtime for s, t in zip(start, tasks))
+    return rec
+
+
+def main():
+    milp, tight, Strategy, pulp = _load_reference()
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import ref_eval as R
+
+    cases = [
+        ("K1_J3_g8_seed1", probe_tuples(3, [8], 1), 60),
+        ("C1_J4_g12_seed0", probe_tuples(4, [1, 2], 0), 60),
+        ("J3_g1248_seed0", probe_tuples(3, [1, 2, 4, 8], 0), 120),
+        ("J4_g1248_seed3", probe_tuples(4, [1, 2, 4, 8], 3), 240),
+        ("J4_g48_seed5", probe_tuples(4, [4, 8], 5), 120),
+        ("J5_g248_seed2", probe_tuples(5, [2, 4, 8], 2), 240),
+        ("H4_hetero_seed7", hetero_tuples(4, 7), 120),
+        ("H5_hetero_seed11", hetero_tuples(5, 11), 240),
+        ("K2_J5_g1248_seed0", probe_tuples(5, [1, 2, 4, 8], 0), 60),
+    ]
+    out = {"generator": "oracle/gen_golden.py", "reference_commit": "b65e3d2",
+           "scipy": __import__("scipy").__version__, "cases": []}
+    for name, tuples, timeout in cases:
+        for variant, mod in (("tight_m", tight), ("as_shipped", milp)):
+            rec = run_case(mod, Strategy, pulp, name, tuples, timeout if variant == "tight_m" else min(timeout, 60))
+            rec["variant"] = variant
+            if rec["incumbent"]:
+                plan = R.plan_from_arrays(tuples, rec["sta"], rec["tga"], rec["bss"], rec["bna"])
+                ok, ov, mk = R.check_plan([p[0] for p in plan], [p[1] for p in plan],
+                                          [p[2] for p in plan], [p[3] for p in plan])
+                rec["overlaps"] = ov
+                rec["feasible"] = bool(ok)
+            rec["proven_optimal"] = bool(rec["highs"].get("status") == 0)
+            # exhaustive list-scheduling optimum for the same instance (oracle side)
+            tab, optmap = R.table_from_tuples(tuples)
+            bf = R.brute_force(tab, optmap, integer_starts=True)
+            rec["bruteforce_int"] = {"makespan": bf[0], "opt": list(bf[1]), "prio": list(bf[2])}
+            bf = R.brute_force(tab, optmap, integer_starts=False)
+            rec["bruteforce_real"] = {"makespan": bf[0], "opt": list(bf[1]), "prio": list(bf[2])}
+            print(name, variant, "status", rec["highs"].get("status"), "mk", rec.get("makespan"),
+                  "bf", rec["bruteforce_int"]["makespan"], "overlaps", rec.get("overlaps"),
+                  "%.1fs" % rec["solver_wall_s"], flush=True)
+            out["cases"].append(rec)
+    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "milp_cases.json")
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,14 @@
+"""saturn_b200 — Blackwell-native SPASE solver hot path behind Saturn's own solver API.
+
+Public surface (mirrors the reference's module layout, see the `saturn/` alias package):
+    saturn_b200.solver.solve / convert_into_comprehensible     <- saturn.solver
+    saturn_b200.orchestrator.orchestrate / forecast            <- saturn.orchestrate, saturn.executor.forecast
+    saturn_b200.representations.Task / HParams / Strategy / Techniques
+    saturn_b200.engine.Engine                                  <- ctypes wrapper of include/saturn_b200.h
+"""
+from .representations import HParams, Strategy, Task, Techniques  # noqa: F401
+from .solver import convert_into_comprehensible, solve  # noqa: F401
+from .orchestrator import forecast, orchestrate  # noqa: F401
+
+__all__ = ["HParams", "Strategy", "Task", "Techniques", "solve", "convert_into_comprehensible", "orchestrate",
+           "forecast"]

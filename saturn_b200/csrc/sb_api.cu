@@ -1,0 +1,564 @@
+// sb_api.cu — the extern "C" boundary declared in include/saturn_b200.h.
+//
+// No exceptions cross this boundary and no CPU fallback exists: every entry point either runs
+// the CUDA path on the handle's device or returns a negative sb_status with sb_last_error() set.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "sb_search.h"
+
+using namespace sb;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(SB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct SearchState {
+  bool ready = false;
+  SearchDev d;
+  sb_search_params p;
+  float scale = 0.f;  // temperature unit: incumbent makespan after initialisation
+  long long evaluated = 0;
+  int rounds_done = 0;
+  uint8_t *cand_o = nullptr, *cand_p = nullptr;  // device scratch for injected candidates
+  void* blocks[16];
+  int nblocks = 0;
+};
+
+struct sb_handle {
+  Device dev;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int J = 0, S = 0;
+  float sentinel = kSentinel;
+  float* tab = nullptr;
+  float* tmin = nullptr;
+  uint8_t* args = nullptr;
+  uint8_t* vopt[2] = {nullptr, nullptr};  // [0] full, [1] reduced
+  int* nvalid[2] = {nullptr, nullptr};
+  std::vector<float> h_tmin;
+  std::vector<uint8_t> h_args;
+  unsigned long long* d_scratch = nullptr;  // 4 x u64
+  // staging for sb_eval_host
+  cudaStream_t hs[2] = {nullptr, nullptr};
+  uint8_t* st_o[2] = {nullptr, nullptr};
+  uint8_t* st_p[2] = {nullptr, nullptr};
+  float* st_mk[2] = {nullptr, nullptr};
+  long long st_cap = 0;
+  size_t st_row_o = 0, st_row_p = 0;
+  // scratch for decode
+  uint8_t* dec_buf = nullptr;
+  size_t dec_cap = 0;
+  SearchState search;
+  int last_path = -1;
+};
+
+static int use_device(sb_handle* h) {
+  if (!h) return fail(SB_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->dev.ordinal));
+  return SB_OK;
+}
+
+static void free_table(sb_handle* h) {
+  cudaFree(h->tab); cudaFree(h->tmin); cudaFree(h->args);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->vopt[i]); cudaFree(h->nvalid[i]); h->vopt[i] = nullptr; h->nvalid[i] = nullptr; }
+  h->tab = h->tmin = nullptr; h->args = nullptr;
+  h->J = h->S = 0;
+}
+
+static void free_search(sb_handle* h) {
+  SearchState& s = h->search;
+  for (int i = 0; i < s.nblocks; ++i) cudaFree(s.blocks[i]);
+  s.nblocks = 0;
+  s.ready = false;
+  s.d = SearchDev();
+  s.cand_o = s.cand_p = nullptr;
+}
+
+static void free_staging(sb_handle* h) {
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->st_o[i]); cudaFree(h->st_p[i]); cudaFree(h->st_mk[i]);
+    h->st_o[i] = h->st_p[i] = nullptr; h->st_mk[i] = nullptr;
+  }
+  h->st_cap = 0;
+}
+
+extern "C" {
+
+int sb_abi_version(void) { return SB_ABI_VERSION; }
+const char* sb_last_error(void) { return g_err; }
+
+int sb_create(int device, void* stream, sb_handle** out) {
+  if (!out) return fail(SB_ERR_ARG, "out is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SB_ERR_CUDA, "no CUDA device available (%s); saturn_b200 has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(SB_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  sb_handle* h = new (std::nothrow) sb_handle();
+  if (!h) return fail(SB_ERR_NOMEM, "out of host memory");
+  h->dev.ordinal = device;
+  h->dev.sm_count = prop.multiProcessorCount;
+  h->dev.smem_optin = prop.sharedMemPerBlockOptin;
+  h->stream = static_cast<cudaStream_t>(stream);  // NULL = the context's default stream
+  e = cudaMalloc(&h->d_scratch, 4 * sizeof(unsigned long long));
+  if (e != cudaSuccess) { sb_destroy(h); return fail(SB_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  for (int i = 0; i < 2; ++i) {
+    e = cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) { sb_destroy(h); return fail(SB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  }
+  *out = h;
+  return SB_OK;
+}
+
+int sb_destroy(sb_handle* h) {
+  if (!h) return SB_OK;
+  cudaSetDevice(h->dev.ordinal);
+  cudaStreamSynchronize(h->stream);
+  free_search(h);
+  free_table(h);
+  free_staging(h);
+  cudaFree(h->d_scratch);
+  cudaFree(h->dec_buf);
+  for (int i = 0; i < 2; ++i)
+    if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SB_OK;
+}
+
+int sb_sync(sb_handle* h) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return SB_OK;
+}
+
+int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int S, int G, int nodes) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (!T || !gcount) return fail(SB_ERR_ARG, "T / gcount is null");
+  if (J < 1 || J > 65535) return fail(SB_ERR_ARG, "J=%d outside 1..65535", J);
+  if (S < 1 || S > SB_MAX_STRATEGIES) return fail(SB_ERR_ARG, "S=%d outside 1..%d", S, SB_MAX_STRATEGIES);
+  if (G < 1 || G > SB_NSLOT) return fail(SB_ERR_ARG, "G=%d outside 1..%d", G, SB_NSLOT);
+  if (nodes != 1) return fail(SB_ERR_UNSUPPORTED, "nodes=%d: only single-node tables are supported", nodes);
+  uint64_t packed = 0;
+  for (int g = 0; g < G; ++g) {
+    if (gcount[g] < 1 || gcount[g] > SB_NSLOT) return fail(SB_ERR_ARG, "gcount[%d]=%d outside 1..8", g, gcount[g]);
+    packed |= static_cast<uint64_t>(gcount[g]) << (8 * g);
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  free_search(h);
+  free_table(h);
+  const size_t nT = static_cast<size_t>(J) * S * G;
+  const size_t ntab = static_cast<size_t>(J) * S * kSlots;
+  CK(cudaMalloc(&h->tab, ntab * sizeof(float)));
+  CK(cudaMalloc(&h->tmin, static_cast<size_t>(J) * kSlots * sizeof(float)));
+  CK(cudaMalloc(&h->args, static_cast<size_t>(J) * kSlots));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&h->vopt[i], static_cast<size_t>(J) * kSlots));
+    CK(cudaMalloc(&h->nvalid[i], static_cast<size_t>(J) * sizeof(int)));
+  }
+  cudaPointerAttributes attr;
+  const float* Tdev = T;
+  float* tmp = nullptr;
+  cudaError_t pe = cudaPointerGetAttributes(&attr, T);
+  const bool on_device = (pe == cudaSuccess) && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  if (pe != cudaSuccess) cudaGetLastError();
+  if (!on_device) {
+    CK(cudaMalloc(&tmp, nT * sizeof(float)));
+    CK(cudaMemcpyAsync(tmp, T, nT * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    Tdev = tmp;
+  }
+  cudaError_t e = build_table_launch(Tdev, J, S, G, packed, h->tab, h->tmin, h->args, h->stream);
+  if (e == cudaSuccess) e = build_valid_launch(h->tmin, h->args, J, 0, h->sentinel, h->vopt[0], h->nvalid[0], h->stream);
+  if (e == cudaSuccess) e = build_valid_launch(h->tmin, h->args, J, 1, h->sentinel, h->vopt[1], h->nvalid[1], h->stream);
+  h->h_tmin.assign(static_cast<size_t>(J) * kSlots, 0.f);
+  h->h_args.assign(static_cast<size_t>(J) * kSlots, 0);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->h_tmin.data(), h->tmin, h->h_tmin.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->h_args.data(), h->args, h->h_args.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (tmp) cudaFree(tmp);
+  if (e != cudaSuccess) {
+    free_table(h);
+    return fail(SB_ERR_CUDA, "building the table failed: %s", cudaGetErrorString(e));
+  }
+  h->J = J;
+  h->S = S;
+  return SB_OK;
+}
+
+int sb_set_sentinel(sb_handle* h, float threshold) {
+  if (!h) return fail(SB_ERR_ARG, "null handle");
+  if (!(threshold > 0.f)) return fail(SB_ERR_ARG, "sentinel threshold must be positive");
+  h->sentinel = threshold;
+  return SB_OK;
+}
+
+int sb_get_reduced(sb_handle* h, float* tmin, uint8_t* args) {
+  if (!h) return fail(SB_ERR_ARG, "null handle");
+  if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
+  if (tmin) memcpy(tmin, h->h_tmin.data(), h->h_tmin.size() * sizeof(float));
+  if (args) memcpy(args, h->h_args.data(), h->h_args.size());
+  return SB_OK;
+}
+
+static int make_call(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride, unsigned flags,
+                     EvalCall* c) {
+  if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
+  if (B < 0) return fail(SB_ERR_ARG, "B=%lld is negative", static_cast<long long>(B));
+  if (B > 0 && (!opt || !prio)) return fail(SB_ERR_ARG, "opt / prio is null");
+  if (row_stride < h->J) return fail(SB_ERR_ARG, "row_stride=%lld < J=%d", static_cast<long long>(row_stride), h->J);
+  if (B > 0xffffffffll) return fail(SB_ERR_ARG, "B=%lld exceeds 2^32-1 candidates per call", static_cast<long long>(B));
+  const int pb = h->J <= 256 ? 1 : 2;
+  const bool reduced = (flags & SB_FLAG_REDUCED) != 0;
+  c->tab = reduced ? h->tmin : h->tab;
+  c->J = h->J;
+  c->SG = (reduced ? 1 : h->S) * kSlots;
+  c->opt = opt;
+  c->prio = static_cast<const uint8_t*>(prio);
+  c->B = B;
+  c->stride_o = row_stride;
+  c->stride_p = row_stride * pb;
+  c->flags = flags;
+  return SB_OK;
+}
+
+int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride, unsigned flags,
+            float* makespan_out, uint64_t* best_key, uint32_t id_base) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  EvalCall c;
+  rc = make_call(h, opt, prio, B, row_stride, flags, &c);
+  if (rc) return rc;
+  if (B > 0 && !makespan_out) return fail(SB_ERR_ARG, "makespan_out is null");
+  c.out = makespan_out;
+  c.best_key = reinterpret_cast<unsigned long long*>(best_key);
+  c.id_base = id_base;
+  c.force_generic = (flags & 0x80000000u) ? 1 : 0;  // test hook: exercise the generic kernel
+  CK(eval_launch(h->dev, c, h->stream, &h->last_path));
+  return SB_OK;
+}
+
+int sb_last_eval_path(sb_handle* h) { return h ? h->last_path : -1; }
+
+int sb_validate(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride, unsigned flags,
+                int64_t* bad_rows) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  EvalCall c;
+  rc = make_call(h, opt, prio, B, row_stride, flags, &c);
+  if (rc) return rc;
+  if (!bad_rows) return fail(SB_ERR_ARG, "bad_rows is null");
+  CK(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long), h->stream));
+  CK(validate_launch(h->dev, c, h->d_scratch, h->stream));
+  unsigned long long bad = 0;
+  CK(cudaMemcpyAsync(&bad, h->d_scratch, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *bad_rows = static_cast<int64_t>(bad);
+  return SB_OK;
+}
+
+int sb_eval_full(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride, unsigned flags,
+                 float* makespan_out, float* start_out, uint32_t* slotmask_out) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  EvalCall c;
+  rc = make_call(h, opt, prio, B, row_stride, flags, &c);
+  if (rc) return rc;
+  c.out = makespan_out;
+  CK(eval_full_launch(h->dev, c, start_out, slotmask_out, h->stream));
+  return SB_OK;
+}
+
+static int ensure_staging(sb_handle* h, long long cap, size_t row_o, size_t row_p) {
+  if (h->st_cap >= cap && h->st_row_o == row_o && h->st_row_p == row_p) return SB_OK;
+  free_staging(h);
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&h->st_o[i], static_cast<size_t>(cap) * row_o));
+    CK(cudaMalloc(&h->st_p[i], static_cast<size_t>(cap) * row_p));
+    CK(cudaMalloc(&h->st_mk[i], static_cast<size_t>(cap) * sizeof(float)));
+  }
+  h->st_cap = cap;
+  h->st_row_o = row_o;
+  h->st_row_p = row_p;
+  return SB_OK;
+}
+
+int sb_eval_host(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride, unsigned flags,
+                 float* makespan_out) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  EvalCall c;
+  rc = make_call(h, opt, prio, B, row_stride, flags, &c);
+  if (rc) return rc;
+  if (B == 0) return SB_OK;
+  if (!makespan_out) return fail(SB_ERR_ARG, "makespan_out is null");
+  // chunk = a few full waves of 32-candidate tiles over all SMs, so copies overlap kernels
+  const long long wave = static_cast<long long>(h->dev.sm_count) * 8 * 32;
+  long long chunk = wave * 4;
+  if (chunk > B) chunk = B;
+  rc = ensure_staging(h, chunk, static_cast<size_t>(c.stride_o), static_cast<size_t>(c.stride_p));
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  const uint8_t* ho = opt;
+  const uint8_t* hp = static_cast<const uint8_t*>(prio);
+  int slot = 0;
+  for (long long b0 = 0; b0 < B; b0 += chunk, slot ^= 1) {
+    const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    cudaStream_t st = h->hs[slot];
+    CK(cudaMemcpyAsync(h->st_o[slot], ho + b0 * c.stride_o, static_cast<size_t>(nb) * c.stride_o, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->st_p[slot], hp + b0 * c.stride_p, static_cast<size_t>(nb) * c.stride_p, cudaMemcpyHostToDevice, st));
+    EvalCall cc = c;
+    cc.opt = h->st_o[slot];
+    cc.prio = h->st_p[slot];
+    cc.B = nb;
+    cc.out = h->st_mk[slot];
+    CK(eval_launch(h->dev, cc, st, &h->last_path));
+    CK(cudaMemcpyAsync(makespan_out + b0, h->st_mk[slot], static_cast<size_t>(nb) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(h->hs[0]));
+  CK(cudaStreamSynchronize(h->hs[1]));
+  return SB_OK;
+}
+
+int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags, float* start, uint32_t* slotmask,
+              uint8_t* strategy, uint8_t* gpus, float* makespan) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
+  if (!opt || !prio) return fail(SB_ERR_ARG, "opt / prio is null");
+  const int J = h->J;
+  const int pb = J <= 256 ? 1 : 2;
+  const size_t need = static_cast<size_t>(J) * (1 + pb) + static_cast<size_t>(J) * 8 + 16 + 64;
+  if (h->dec_cap < need) {
+    cudaFree(h->dec_buf);
+    h->dec_buf = nullptr;
+    h->dec_cap = 0;
+    CK(cudaMalloc(&h->dec_buf, need));
+    h->dec_cap = need;
+  }
+  // layout: [start f32 J][mask u32 J][mk f32 (16B)][opt J][prio J*pb]
+  float* d_start = reinterpret_cast<float*>(h->dec_buf);
+  uint32_t* d_mask = reinterpret_cast<uint32_t*>(h->dec_buf + static_cast<size_t>(J) * 4);
+  float* d_mk = reinterpret_cast<float*>(h->dec_buf + static_cast<size_t>(J) * 8);
+  uint8_t* d_opt = h->dec_buf + static_cast<size_t>(J) * 8 + 16;
+  uint8_t* d_prio = d_opt + ((J + 1) & ~1);
+  CK(cudaMemcpyAsync(d_opt, opt, J, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_prio, prio, static_cast<size_t>(J) * pb, cudaMemcpyHostToDevice, h->stream));
+  EvalCall c;
+  rc = make_call(h, d_opt, d_prio, 1, J, flags, &c);
+  if (rc) return rc;
+  c.out = d_mk;
+  CK(eval_full_launch(h->dev, c, d_start, d_mask, h->stream));
+  std::vector<float> hs(J);
+  std::vector<uint32_t> hm(J);
+  float mk = 0.f;
+  CK(cudaMemcpyAsync(hs.data(), d_start, static_cast<size_t>(J) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hm.data(), d_mask, static_cast<size_t>(J) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&mk, d_mk, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const bool reduced = (flags & SB_FLAG_REDUCED) != 0;
+  for (int j = 0; j < J; ++j) {
+    if (start) start[j] = hs[j];
+    if (slotmask) slotmask[j] = hm[j];
+    const int col = opt[j] & 7;
+    if (gpus) gpus[j] = static_cast<uint8_t>(col + 1);
+    if (strategy) strategy[j] = reduced ? h->h_args[static_cast<size_t>(j) * kSlots + col] : static_cast<uint8_t>(opt[j] >> 3);
+  }
+  if (makespan) *makespan = mk;
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ search
+static int search_alloc(SearchState& s, void** p, size_t bytes) {
+  if (s.nblocks >= 16) return fail(SB_ERR_NOMEM, "search block table full");
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return fail(SB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  s.blocks[s.nblocks++] = *p;
+  return SB_OK;
+}
+
+static int search_eval(sb_handle* h, bool cur_rows, long long first, long long count) {
+  SearchState& s = h->search;
+  EvalCall c;
+  const uint8_t* ro = (cur_rows ? s.d.cur_o : s.d.prop_o) + first * s.d.stride_o;
+  const uint8_t* rp = (cur_rows ? s.d.cur_p : s.d.prop_p) + first * s.d.stride_p;
+  int rc = make_call(h, ro, rp, count, s.d.stride_o, s.p.flags, &c);
+  if (rc) return rc;
+  c.out = (cur_rows ? s.d.cur_mk : s.d.prop_mk) + first;
+  c.best_key = s.d.keys;
+  c.id_base = static_cast<uint32_t>(s.d.chain_base + static_cast<uint64_t>(first));
+  CK(eval_launch(h->dev, c, h->stream, &h->last_path));
+  return SB_OK;
+}
+
+int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_opt, const void* warm_prio) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
+  if (!p) return fail(SB_ERR_ARG, "params is null");
+  if (p->chains < 1 || p->chains > (1ll << 31)) return fail(SB_ERR_ARG, "chains=%lld out of range", (long long)p->chains);
+  CK(cudaStreamSynchronize(h->stream));
+  free_search(h);
+  SearchState& s = h->search;
+  s.p = *p;
+  if (s.p.total_rounds < 1) s.p.total_rounds = 1;
+  const int J = h->J;
+  const int pb = J <= 256 ? 1 : 2;
+  SearchDev& d = s.d;
+  d.J = J;
+  d.pb = pb;
+  d.chains = p->chains;
+  d.chain_base = p->chain_base;
+  d.seed = p->seed;
+  d.stride_o = (J + 15) & ~15;
+  d.stride_p = (J * pb + 15) & ~15;
+  // make stride_p == stride_o * pb so that one element stride describes both (sb_eval contract)
+  d.stride_p = d.stride_o * pb;
+  const bool reduced = (p->flags & SB_FLAG_REDUCED) != 0;
+  d.vopt = h->vopt[reduced ? 1 : 0];
+  d.nvalid = h->nvalid[reduced ? 1 : 0];
+  const size_t P = static_cast<size_t>(d.chains);
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_o), P * d.stride_o))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_p), P * d.stride_p))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_o), P * d.stride_o))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_p), P * d.stride_p))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_mk), P * sizeof(float)))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_mk), P * sizeof(float)))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.keys), 2 * sizeof(unsigned long long)))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_o), d.stride_o))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_p), d.stride_p))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_o), d.stride_o))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_p), d.stride_p))) return rc;
+  CK(cudaMemsetAsync(d.keys, 0xff, 2 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(d.cur_o, 0, P * d.stride_o, h->stream));
+  CK(cudaMemsetAsync(d.cur_p, 0, P * d.stride_p, h->stream));
+  CK(search_init_population(d, h->stream));
+  s.ready = true;
+  if (warm_opt && warm_prio) {
+    CK(cudaMemsetAsync(s.cand_o, 0, d.stride_o, h->stream));
+    CK(cudaMemsetAsync(s.cand_p, 0, d.stride_p, h->stream));
+    CK(cudaMemcpyAsync(s.cand_o, warm_opt, J, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(s.cand_p, warm_prio, static_cast<size_t>(J) * pb, cudaMemcpyHostToDevice, h->stream));
+    CK(search_inject(d, s.cand_o, s.cand_p, 0, 1, h->stream));
+  }
+  if ((rc = search_eval(h, true, 0, d.chains))) return rc;
+  CK(search_keep_best(d, true, h->stream));
+  unsigned long long key = 0;
+  CK(cudaMemcpyAsync(&key, d.keys, sizeof(key), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  uint32_t bits = static_cast<uint32_t>(key >> 32);
+  float mk;
+  memcpy(&mk, &bits, 4);
+  s.scale = isfinite(mk) ? mk : 1.0f;
+  s.evaluated = d.chains;
+  s.rounds_done = 0;
+  return SB_OK;
+}
+
+int sb_search_round(sb_handle* h, int rounds) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  for (int r = 0; r < rounds; ++r) {
+    const int round = s.rounds_done + 1;
+    float frac = static_cast<float>(round - 1) / static_cast<float>(s.p.total_rounds > 1 ? s.p.total_rounds - 1 : 1);
+    if (frac > 1.f) frac = 1.f;
+    float tf;
+    if (s.p.t_start <= 0.f) tf = 0.f;
+    else if (s.p.t_end <= 0.f) tf = s.p.t_start * (1.f - frac);
+    else tf = s.p.t_start * powf(s.p.t_end / s.p.t_start, frac);
+    const float temperature = tf * s.scale;
+    CK(search_propose(s.d, round, h->stream));
+    if ((rc = search_eval(h, false, 0, s.d.chains))) return rc;
+    CK(search_keep_best(s.d, false, h->stream));
+    CK(search_accept(s.d, round, temperature, h->stream));
+    s.rounds_done = round;
+    s.evaluated += s.d.chains;
+  }
+  return SB_OK;
+}
+
+int sb_search_best_key_ptr(sb_handle* h, uint64_t** key_dev) {
+  if (!h || !key_dev) return fail(SB_ERR_ARG, "null argument");
+  if (!h->search.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  *key_dev = reinterpret_cast<uint64_t*>(h->search.d.keys);
+  return SB_OK;
+}
+
+int sb_search_best(sb_handle* h, uint8_t* opt, void* prio, float* makespan, uint64_t* key_out) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  unsigned long long keys[2];
+  CK(cudaMemcpyAsync(keys, s.d.keys, sizeof(keys), cudaMemcpyDeviceToHost, h->stream));
+  if (opt) CK(cudaMemcpyAsync(opt, s.d.best_o, s.d.J, cudaMemcpyDeviceToHost, h->stream));
+  if (prio) CK(cudaMemcpyAsync(prio, s.d.best_p, static_cast<size_t>(s.d.J) * s.d.pb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (makespan) {
+    uint32_t bits = static_cast<uint32_t>(keys[1] >> 32);
+    memcpy(makespan, &bits, 4);
+  }
+  if (key_out) *key_out = keys[1];
+  return SB_OK;
+}
+
+int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int copies) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  if (!opt || !prio) return fail(SB_ERR_ARG, "opt / prio is null");
+  if (copies < 1) return SB_OK;
+  if (copies > s.d.chains) copies = static_cast<int>(s.d.chains);
+  const long long first = s.d.chains - copies;
+  CK(cudaMemsetAsync(s.cand_o, 0, s.d.stride_o, h->stream));
+  CK(cudaMemsetAsync(s.cand_p, 0, s.d.stride_p, h->stream));
+  CK(cudaMemcpyAsync(s.cand_o, opt, s.d.J, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(s.cand_p, prio, static_cast<size_t>(s.d.J) * s.d.pb, cudaMemcpyHostToDevice, h->stream));
+  CK(search_inject(s.d, s.cand_o, s.cand_p, first, copies, h->stream));
+  if ((rc = search_eval(h, true, first, copies))) return rc;
+  CK(search_keep_best(s.d, true, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // opt / prio are caller memory: do not return with copies in flight
+  s.evaluated += copies;
+  return SB_OK;
+}
+
+int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done) {
+  if (!h) return fail(SB_ERR_ARG, "null handle");
+  if (evaluated) *evaluated = h->search.evaluated;
+  if (rounds_done) *rounds_done = h->search.rounds_done;
+  return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// sb_common.cuh — shared device helpers for the SPASE candidate evaluator (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/saturn_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "saturn_b200 kernels target sm_100a (B200) only"
+#endif
+
+namespace sb {
+
+constexpr int kSlots = SB_NSLOT;
+constexpr int kWarp = 32;
+constexpr float kSentinel = 1.0e6f;  // reference's "unprofiled" runtime, PerformanceEvaluator.py:99
+
+__device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
+
+// ---------------------------------------------------------------- mbarrier + TMA bulk copy (1-D)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  // make the inits visible to the async proxy (the TMA unit) before any bulk copy signals them
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a barrier that never completes is a bug (wrong byte count / misaligned copy);
+// trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+// global -> shared bulk copy through the TMA unit; completion is signalled on `bar` as `bytes`
+// of transaction count.  dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------- the list-scheduling step
+// State: the 8 slot ready-times kept SORTED ascending in registers (f[0] <= ... <= f[7]).  Which
+// physical slot holds which time does not influence any start time or the makespan (ties are
+// between equal values), so the hot kernel evolves the sorted multiset only; the slot-exact
+// variant lives in k_eval_full.
+//
+// A job with k = km1 + 1 GPUs starts at s = f[km1] (the k-th smallest), and the k smallest
+// entries are replaced by v = s + hold.  With sh[i] = f[i + k] (+inf past the end) the new sorted
+// state is  f'[i] = max(f[i], min(v, sh[i]))  — every surviving element below v moves down k
+// places, the k copies of v follow, larger elements stay.  sh is produced by a 3-stage barrel
+// shifter on the bits of km1 (24 selects), no dynamic register indexing and no divergence.
+template <bool kIntegerStarts>
+__device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1) {
+  const float INF = inf_f();
+  const bool b2 = (km1 & 4) != 0, b1 = (km1 & 2) != 0, b0 = (km1 & 1) != 0;
+  float x0 = b2 ? f[4] : f[0], x1 = b2 ? f[5] : f[1], x2 = b2 ? f[6] : f[2], x3 = b2 ? f[7] : f[3];
+  float x4 = b2 ? INF : f[4], x5 = b2 ? INF : f[5], x6 = b2 ? INF : f[6], x7 = b2 ? INF : f[7];
+  float y0 = b1 ? x2 : x0, y1 = b1 ? x3 : x1, y2 = b1 ? x4 : x2, y3 = b1 ? x5 : x3;
+  float y4 = b1 ? x6 : x4, y5 = b1 ? x7 : x5, y6 = b1 ? INF : x6, y7 = b1 ? INF : x7;
+  float z0 = b0 ? y1 : y0, z1 = b0 ? y2 : y1, z2 = b0 ? y3 : y2, z3 = b0 ? y4 : y3;
+  float z4 = b0 ? y5 : y4, z5 = b0 ? y6 : y5, z6 = b0 ? y7 : y6, z7 = b0 ? INF : y7;
+  const float s = z0;  // = f[km1]
+  float v;
+  if (kIntegerStarts) {
+    // every entry of f is an integer here, so s is; the slot is usable again at s + ceil(rt)
+    v = s + ceilf(rt);
+    mk = fmaxf(mk, s + rt);
+  } else {
+    v = s + rt;
+  }
+  f[0] = fmaxf(f[0], fminf(v, z1));
+  f[1] = fmaxf(f[1], fminf(v, z2));
+  f[2] = fmaxf(f[2], fminf(v, z3));
+  f[3] = fmaxf(f[3], fminf(v, z4));
+  f[4] = fmaxf(f[4], fminf(v, z5));
+  f[5] = fmaxf(f[5], fminf(v, z6));
+  f[6] = fmaxf(f[6], fminf(v, z7));
+  f[7] = fmaxf(f[7], v);
+}
+
+__device__ __forceinline__ unsigned long long pack_key(float mk, uint32_t id) {
+  return (static_cast<unsigned long long>(__float_as_uint(mk)) << 32) | id;
+}
+
+// counter-based RNG: one 64-bit mix per draw, keyed by (seed, stream id, counter)
+__device__ __host__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__device__ __host__ __forceinline__ uint64_t rng_u64(uint64_t seed, uint64_t stream, uint64_t ctr) {
+  return mix64(mix64(seed ^ (stream * 0xd1342543de82ef95ull)) + ctr * 0x2545f4914f6cdd1dull);
+}
+
+}  // namespace sb

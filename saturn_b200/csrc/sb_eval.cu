@@ -1,0 +1,427 @@
+// sb_eval.cu — makespan evaluation of list-schedule candidates (the measured hot kernel).
+//
+// Replaces the arithmetic the reference hands to Gurobi/CBC (saturn/solver/milp.py:321-327):
+// instead of branch-and-bound over the MILP of milp.py:96-319, B candidates
+// (option vector, priority permutation) are scored in parallel; each score is the makespan the
+// MILP's constraints would force for that choice of strategies / GPU counts / ordering.
+//
+// Kernel shape (k_eval_tiles):
+//   * persistent grid, one CTA per SM, NW warps per CTA; the J x S x 8 runtime table is staged
+//     once per CTA into shared memory with TMA bulk copies (cp.async.bulk + mbarrier);
+//   * each warp owns a tile of 32 candidates: every lane fetches ITS candidate's opt row and
+//     prio row with one TMA bulk copy each into a padded shared-memory row (row stride = odd
+//     multiple of 16 B, so per-lane 128-bit reads are bank-conflict free), completion on a
+//     per-warp mbarrier — no CTA-wide barrier after start-up;
+//   * one candidate per LANE: the 8 slot ready-times live sorted in 8 registers and one
+//     scheduling step is ~45 predicated selects / min / max (sb_common.cuh: ls_step) — fp32
+//     min/max/add and byte indexing only, no tensor cores;
+//   * makespans are written coalesced (128 B per warp); an optional 64-bit arg-min key is
+//     folded with one redux + one atomicMin per warp.
+#include "sb_internal.h"
+
+namespace sb {
+
+struct TileArgs {
+  const float* tab;  // [J][SG] fp32, SG = S*8
+  int J, SG;
+  const uint8_t* opt;
+  const uint8_t* prio;
+  long long B;
+  long long stride_o, stride_p;  // bytes between candidate rows in global memory
+  int row_o, row_p;              // shared-memory row strides (bytes, odd multiple of 16)
+  int copy_o, copy_p;            // bytes per row copy (multiple of 16)
+  int use_bulk;                  // rows are 16-byte aligned -> TMA bulk copies
+  float* out;
+  unsigned long long* best_key;
+  uint32_t id_base;
+  long long ntiles;
+};
+
+template <int PB>
+__device__ __forceinline__ int prio_at(const uint32_t (&w)[4], int t) {
+  if (PB == 1) return (w[t >> 2] >> ((t & 3) * 8)) & 0xff;
+  return (w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
+}
+
+template <int PB, bool INT>
+__global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tab_bytes = static_cast<uint32_t>(a.J) * a.SG * 4u;
+  float* tab_s = reinterpret_cast<float*>(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((tab_bytes + 15u) & ~15u));
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(bars) + (((1 + nw) * 8 + 15) & ~15);
+  const uint32_t tile_bytes = 32u * (a.row_o + a.row_p);
+  uint8_t* tile_o = tiles + static_cast<size_t>(warp) * tile_bytes;
+  uint8_t* tile_p = tile_o + 32u * a.row_o;
+  uint64_t* bar_tab = bars;
+  uint64_t* bar_w = bars + 1 + warp;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_tab, 1);
+    for (int w = 0; w < nw; ++w) mbar_init(bars + 1 + w, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // stage the runtime table: TMA bulk copies of <= 32 KB each, one mbarrier phase
+    mbar_arrive_expect_tx(bar_tab, tab_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab);
+    for (uint32_t off = 0; off < tab_bytes; off += 32768u) {
+      uint32_t n = min(32768u, tab_bytes - off);
+      tma_bulk_g2s(smem + off, src + off, n, bar_tab);
+    }
+  }
+
+  uint32_t phase = 0;
+  bool tab_ready = false;
+  for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
+       tile += static_cast<long long>(gridDim.x) * nw) {
+    const long long b0 = tile * 32;
+    const int nb = static_cast<int>(min(32ll, a.B - b0));
+    const bool active = lane < nb;
+    // ---- fetch this warp's 32 candidate rows
+    __syncwarp();
+    if (a.use_bulk) {
+      fence_proxy_async();  // order the previous tile's generic-proxy reads before async writes
+      if (lane == 0) mbar_arrive_expect_tx(bar_w, static_cast<uint32_t>(nb) * (a.copy_o + a.copy_p));
+      __syncwarp();
+      if (active) {
+        tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + (b0 + lane) * a.stride_o, a.copy_o, bar_w);
+        tma_bulk_g2s(tile_p + lane * a.row_p, a.prio + (b0 + lane) * a.stride_p, a.copy_p, bar_w);
+      }
+      mbar_wait(bar_w, phase);
+      phase ^= 1;
+    } else {
+      for (int r = 0; r < nb; ++r) {
+        const uint8_t* so = a.opt + (b0 + r) * a.stride_o;
+        const uint8_t* sp = a.prio + (b0 + r) * a.stride_p;
+        for (int x = lane; x < a.J; x += 32) tile_o[r * a.row_o + x] = so[x];
+        for (int x = lane; x < a.J * PB; x += 32) tile_p[r * a.row_p + x] = sp[x];
+      }
+      __syncwarp();
+    }
+    if (!tab_ready) {
+      mbar_wait(bar_tab, 0);
+      tab_ready = true;
+    }
+    // ---- one candidate per lane
+    float mk = 0.f;
+    if (active) {
+      const uint8_t* orow = tile_o + lane * a.row_o;
+      const uint4* prow = reinterpret_cast<const uint4*>(tile_p + lane * a.row_p);
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      constexpr int STEPS = 16 / PB;  // jobs per 128-bit prio read
+      const int nfull = a.J / STEPS;
+      const int SG = a.SG;
+      for (int c = 0; c < nfull; ++c) {
+        const uint4 p = prow[c];
+        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int t = 0; t < STEPS; ++t) {
+          const int j = prio_at<PB>(w, t);
+          const int o = orow[j];
+          const float rt = tab_s[j * SG + o];
+          ls_step<INT>(f, mk, rt, o & 7);
+        }
+      }
+      const int rem = a.J - nfull * STEPS;
+      if (rem > 0) {
+        const uint4 p = prow[nfull];
+        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int t = 0; t < STEPS; ++t) {
+          if (t < rem) {
+            const int j = prio_at<PB>(w, t);
+            const int o = orow[j];
+            const float rt = tab_s[j * SG + o];
+            ls_step<INT>(f, mk, rt, o & 7);
+          }
+        }
+      }
+      if (!INT) mk = f[7];
+      a.out[b0 + lane] = mk;
+    }
+    if (a.best_key != nullptr) {
+      const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
+      const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+      const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
+      if (lane == __ffs(who) - 1 && active) {
+        const unsigned long long key = pack_key(mk, a.id_base + static_cast<uint32_t>(b0 + lane));
+        if (key < *reinterpret_cast<volatile unsigned long long*>(a.best_key)) atomicMin(a.best_key, key);
+      }
+    }
+  }
+  if (!tab_ready && threadIdx.x == 0) mbar_wait(bar_tab, 0);  // never leave a bulk copy in flight
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic fallback: any J (prio u8/u16), any row stride; rows are read straight from global
+// memory through L1.  The table is staged in shared memory when it fits, else read via L1/L2.
+struct GenericArgs {
+  const float* tab;
+  int J, SG;
+  const uint8_t* opt;
+  const uint8_t* prio;
+  long long B;
+  long long stride_o, stride_p;
+  float* out;
+  unsigned long long* best_key;
+  uint32_t id_base;
+  int tab_in_smem;
+};
+
+template <int PB, bool INT>
+__global__ void __launch_bounds__(128) k_eval_generic(const GenericArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const float* tab = a.tab;
+  if (a.tab_in_smem) {
+    float* tab_s = reinterpret_cast<float*>(smem);
+    const int n = a.J * a.SG;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tab_s[i] = a.tab[i];
+    __syncthreads();
+    tab = tab_s;
+  }
+  const int lane = threadIdx.x & 31;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long Bpad = (a.B + 31) & ~31ll;
+  for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < Bpad; b += nthreads) {
+    const bool active = b < a.B;
+    float mk = 0.f;
+    if (active) {
+      const uint8_t* orow = a.opt + b * a.stride_o;
+      const uint8_t* prow = a.prio + b * a.stride_p;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < a.J; ++i) {
+        const int j = PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i];
+        const int o = orow[j];
+        const float rt = tab[j * a.SG + o];
+        ls_step<INT>(f, mk, rt, o & 7);
+      }
+      if (!INT) mk = f[7];
+      a.out[b] = mk;
+    }
+    if (a.best_key != nullptr) {
+      const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
+      const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+      const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
+      if (lane == __ffs(who) - 1 && active) {
+        const unsigned long long key = pack_key(mk, a.id_base + static_cast<uint32_t>(b));
+        if (key < *reinterpret_cast<volatile unsigned long long*>(a.best_key)) atomicMin(a.best_key, key);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Slot-exact evaluation: start time and GPU-slot bitmask per job.  The k slots with smallest
+// (ready, slot) are found by k ascending scans with a strict '<' (lowest slot wins ties),
+// exactly as the oracle states the rule.  Not a throughput kernel: used to decode winners and
+// for the slot-index parity tests.
+struct FullArgs {
+  const float* tab;
+  int J, SG;
+  const uint8_t* opt;
+  const uint8_t* prio;
+  long long B;
+  long long stride_o, stride_p;
+  float* out;
+  float* start;         // [B][J] by job, nullable
+  uint32_t* slotmask;   // [B][J] by job, nullable
+};
+
+template <int PB, bool INT>
+__global__ void __launch_bounds__(128) k_eval_full(const FullArgs a) {
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < a.B; b += nthreads) {
+    const uint8_t* orow = a.opt + b * a.stride_o;
+    const uint8_t* prow = a.prio + b * a.stride_p;
+    float ready[kSlots];
+#pragma unroll
+    for (int g = 0; g < kSlots; ++g) ready[g] = 0.f;
+    float mk = 0.f;
+    for (int i = 0; i < a.J; ++i) {
+      const int j = PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i];
+      const int o = orow[j];
+      const int k = (o & 7) + 1;
+      const float rt = __ldg(a.tab + static_cast<size_t>(j) * a.SG + o);
+      uint32_t taken = 0;
+      float s = 0.f;
+      for (int q = 0; q < k; ++q) {
+        int best = -1;
+        float bv = 0.f;
+#pragma unroll
+        for (int g = 0; g < kSlots; ++g) {
+          const bool free_slot = ((taken >> g) & 1u) == 0u;
+          if (free_slot && (best < 0 || ready[g] < bv)) {
+            best = g;
+            bv = ready[g];
+          }
+        }
+        taken |= 1u << best;
+        s = bv;  // scans return non-decreasing values: the last one is the k-th smallest
+      }
+      const float hold = (INT && isfinite(rt)) ? ceilf(rt) : rt;
+      const float nxt = s + hold;
+#pragma unroll
+      for (int g = 0; g < kSlots; ++g)
+        if ((taken >> g) & 1u) ready[g] = nxt;
+      mk = fmaxf(mk, s + rt);
+      if (a.start) a.start[b * a.J + j] = s;
+      if (a.slotmask) a.slotmask[b * a.J + j] = taken;
+    }
+    if (a.out) a.out[b] = mk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// validation of external candidates: prio rows are permutations of 0..J-1 and every opt byte
+// names an existing (finite) table cell.  bad[0] counts offending rows.
+__global__ void k_validate(const float* tab, int J, int SG, const uint8_t* opt, const uint8_t* prio, int pb,
+                           long long B, long long stride_o, long long stride_p, unsigned long long* bad) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  extern __shared__ uint32_t seen_all[];
+  const int words = (J + 31) / 32;
+  uint32_t* seen = seen_all + (threadIdx.x >> 5) * words;
+  for (long long b = warp; b < B; b += nwarps) {
+    for (int w = lane; w < words; w += 32) seen[w] = 0;
+    __syncwarp();
+    bool ok = true;
+    const uint8_t* orow = opt + b * stride_o;
+    const uint8_t* prow = prio + b * stride_p;
+    for (int i = lane; i < J; i += 32) {
+      const int j = pb == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i];
+      if (j >= J) {
+        ok = false;
+      } else {
+        const uint32_t old = atomicOr(&seen[j >> 5], 1u << (j & 31));
+        if (old & (1u << (j & 31))) ok = false;
+      }
+      const int o = orow[i];
+      if (o >= SG || !isfinite(tab[static_cast<size_t>(i) * SG + o])) ok = false;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok && lane == 0) atomicAdd(bad, 1ull);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int round_row(int bytes) {
+  int r16 = (bytes + 15) / 16;
+  if ((r16 & 1) == 0) r16 += 1;  // odd multiple of 16 B -> conflict-free per-lane 128-bit reads
+  return r16 * 16;
+}
+
+int plan_tiles(const Device& dev, int J, int SG, int pb, TilePlan* tp) {
+  tp->row_o = round_row(J);
+  tp->row_p = round_row(J * pb);
+  tp->copy_o = (J + 15) & ~15;
+  tp->copy_p = (J * pb + 15) & ~15;
+  const size_t tab_bytes = (static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15);
+  const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + tp->row_p);
+  int nw = 8;
+  while (nw > 0 && tab_bytes + 16 * ((1 + nw + 1) / 2) + nw * per_warp > dev.smem_optin) --nw;
+  tp->warps = nw;
+  tp->smem = tab_bytes + (((1 + nw) * 8 + 15) & ~15) + nw * per_warp;
+  return nw;
+}
+
+template <int PB, bool INT>
+static cudaError_t launch_tiles(const Device& dev, const TileArgs& a, const TilePlan& tp, cudaStream_t st) {
+  auto kern = k_eval_tiles<PB, INT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
+  if (e != cudaSuccess) return e;
+  long long ctas = (a.ntiles + tp.warps - 1) / tp.warps;
+  int grid = static_cast<int>(ctas < dev.sm_count ? ctas : dev.sm_count);
+  kern<<<grid, tp.warps * 32, tp.smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int PB, bool INT>
+static cudaError_t launch_generic(const Device& dev, const GenericArgs& a0, cudaStream_t st) {
+  GenericArgs a = a0;
+  auto kern = k_eval_generic<PB, INT>;
+  size_t tab_bytes = static_cast<size_t>(a.J) * a.SG * 4;
+  size_t smem = 0;
+  a.tab_in_smem = 0;
+  if (tab_bytes <= dev.smem_optin / 2) {
+    a.tab_in_smem = 1;
+    smem = tab_bytes;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  long long blocks = (a.B + 127) / 128;
+  long long cap = static_cast<long long>(dev.sm_count) * 8;
+  int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  if (grid < 1) grid = 1;
+  kern<<<grid, 128, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used) {
+  if (c.B <= 0) return cudaSuccess;
+  const int pb = c.J <= 256 ? 1 : 2;
+  const bool ints = (c.flags & SB_FLAG_INTEGER_STARTS) != 0;
+  TilePlan tp;
+  int nw = c.force_generic ? 0 : plan_tiles(dev, c.J, c.SG, pb, &tp);
+  if (nw >= 2) {
+    TileArgs a;
+    a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
+    a.stride_o = c.stride_o; a.stride_p = c.stride_p;
+    a.row_o = tp.row_o; a.row_p = tp.row_p; a.copy_o = tp.copy_o; a.copy_p = tp.copy_p;
+    a.use_bulk = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
+                 (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0) &&
+                 (c.stride_o >= tp.copy_o) && (c.stride_p >= tp.copy_p);
+    a.out = c.out; a.best_key = c.best_key; a.id_base = c.id_base;
+    a.ntiles = (c.B + 31) / 32;
+    if (path_used) *path_used = a.use_bulk ? 2 : 1;
+    if (pb == 1) return ints ? launch_tiles<1, true>(dev, a, tp, st) : launch_tiles<1, false>(dev, a, tp, st);
+    return ints ? launch_tiles<2, true>(dev, a, tp, st) : launch_tiles<2, false>(dev, a, tp, st);
+  }
+  GenericArgs g;
+  g.tab = c.tab; g.J = c.J; g.SG = c.SG; g.opt = c.opt; g.prio = c.prio; g.B = c.B;
+  g.stride_o = c.stride_o; g.stride_p = c.stride_p; g.out = c.out; g.best_key = c.best_key;
+  g.id_base = c.id_base; g.tab_in_smem = 0;
+  if (path_used) *path_used = 0;
+  if (pb == 1) return ints ? launch_generic<1, true>(dev, g, st) : launch_generic<1, false>(dev, g, st);
+  return ints ? launch_generic<2, true>(dev, g, st) : launch_generic<2, false>(dev, g, st);
+}
+
+cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st) {
+  if (c.B <= 0) return cudaSuccess;
+  const int pb = c.J <= 256 ? 1 : 2;
+  const bool ints = (c.flags & SB_FLAG_INTEGER_STARTS) != 0;
+  FullArgs a;
+  a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
+  a.stride_o = c.stride_o; a.stride_p = c.stride_p; a.out = c.out; a.start = start; a.slotmask = slotmask;
+  long long blocks = (c.B + 127) / 128;
+  long long cap = static_cast<long long>(dev.sm_count) * 16;
+  int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  if (pb == 1) {
+    if (ints) k_eval_full<1, true><<<grid, 128, 0, st>>>(a);
+    else k_eval_full<1, false><<<grid, 128, 0, st>>>(a);
+  } else {
+    if (ints) k_eval_full<2, true><<<grid, 128, 0, st>>>(a);
+    else k_eval_full<2, false><<<grid, 128, 0, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st) {
+  if (c.B <= 0) return cudaSuccess;
+  const int pb = c.J <= 256 ? 1 : 2;
+  const int words = (c.J + 31) / 32;
+  const int threads = 128;
+  size_t smem = static_cast<size_t>(threads / 32) * words * 4;
+  long long blocks = (c.B + 3) / 4;
+  long long cap = static_cast<long long>(dev.sm_count) * 8;
+  int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  k_validate<<<grid, threads, smem, st>>>(c.tab, c.J, c.SG, c.opt, c.prio, pb, c.B, c.stride_o, c.stride_p, bad);
+  return cudaGetLastError();
+}
+
+}  // namespace sb

@@ -1,0 +1,48 @@
+// sb_internal.h — host-side structures shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+struct Device {
+  int ordinal = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;  // max dynamic shared memory per CTA (227 KB on B200)
+};
+
+struct TilePlan {
+  int warps = 0;
+  int row_o = 0, row_p = 0, copy_o = 0, copy_p = 0;
+  size_t smem = 0;
+};
+
+struct EvalCall {
+  const float* tab = nullptr;  // canonical table actually used (full or reduced)
+  int J = 0, SG = 0;
+  const uint8_t* opt = nullptr;
+  const uint8_t* prio = nullptr;
+  long long B = 0;
+  long long stride_o = 0, stride_p = 0;  // bytes
+  unsigned flags = 0;
+  float* out = nullptr;
+  unsigned long long* best_key = nullptr;
+  uint32_t id_base = 0;
+  int force_generic = 0;
+};
+
+int plan_tiles(const Device& dev, int J, int SG, int pb, TilePlan* tp);
+cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used);
+cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st);
+cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st);
+
+// table construction (sb_table.cu)
+cudaError_t build_table_launch(const float* T, int J, int S, int G, uint64_t gcount_packed, float* tab, float* tmin,
+                               uint8_t* args, cudaStream_t st);
+// valid (non-dominated, non-sentinel) option lists for the search: vopt[J][8] opt bytes, nvalid[J]
+cudaError_t build_valid_launch(const float* tmin, const uint8_t* args, int J, int reduced, float sentinel, uint8_t* vopt,
+                               int* nvalid, cudaStream_t st);
+
+}  // namespace sb

@@ -1,0 +1,28 @@
+// sb_search.h — device-resident state of one search population.
+#pragma once
+#include "sb_internal.h"
+
+namespace sb {
+
+struct SearchDev {
+  int J = 0, pb = 1;
+  long long chains = 0;
+  uint64_t chain_base = 0;
+  uint64_t seed = 0;
+  long long stride_o = 0, stride_p = 0;  // bytes, multiples of 16
+  uint8_t *cur_o = nullptr, *cur_p = nullptr, *prop_o = nullptr, *prop_p = nullptr;
+  float *cur_mk = nullptr, *prop_mk = nullptr;
+  const uint8_t* vopt = nullptr;  // [J][8]
+  const int* nvalid = nullptr;    // [J]
+  unsigned long long* keys = nullptr;  // [0] best key of this population, [1] key of the saved encoding
+  uint8_t *best_o = nullptr, *best_p = nullptr;
+};
+
+cudaError_t search_init_population(const SearchDev& s, cudaStream_t st);
+cudaError_t search_propose(const SearchDev& s, int round, cudaStream_t st);
+cudaError_t search_keep_best(const SearchDev& s, bool from_cur, cudaStream_t st);
+cudaError_t search_accept(const SearchDev& s, int round, float temperature, cudaStream_t st);
+cudaError_t search_inject(const SearchDev& s, const uint8_t* cand_o, const uint8_t* cand_p, long long first,
+                          int copies, cudaStream_t st);
+
+}  // namespace sb

@@ -1,0 +1,290 @@
+"""Host-side wrapper of the C ABI (include/saturn_b200.h) over torch tensors.
+
+PyTorch is used only as plumbing here: device memory (`torch.Tensor.data_ptr()`), the current
+CUDA stream, and `torch.distributed` for the per-round MIN all-reduce.  All arithmetic runs in
+the hand-written kernels of saturn_b200/csrc.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FLAG_INTEGER_STARTS, FLAG_REDUCED, SaturnB200Error, SearchParams, check
+
+NSLOT = 8
+
+
+def _flags(integer_starts: bool, reduced: bool) -> int:
+    return (FLAG_INTEGER_STARTS if integer_starts else 0) | (FLAG_REDUCED if reduced else 0)
+
+
+class Engine:
+    """One solver handle bound to one CUDA device."""
+
+    def __init__(self, device: int | torch.device | None = None, stream: Optional[torch.cuda.Stream] = None):
+        self._h = C.c_void_p()
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise SaturnB200Error("no CUDA device is visible; saturn_b200 has no CPU path")
+        if device is None:
+            device = torch.cuda.current_device()
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.device = dev
+        self._lib = lib
+        if stream is None:
+            stream = torch.cuda.current_stream(dev)
+        self._stream = stream
+        sptr = C.c_void_p(stream.cuda_stream) if stream.cuda_stream else None
+        check(lib.sb_create(dev.index or 0, sptr, C.byref(self._h)))
+        self.J = 0
+        self.S = 0
+        self.G = 0
+        self.gcount = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if self._h:
+            self._lib.sb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self._lib.sb_sync(self._h))
+
+    # ------------------------------------------------------------------ table
+    def set_table(self, T, gcount: Optional[Sequence[int]] = None, sentinel: Optional[float] = None):
+        """T[J][S][G] fp32 (numpy array or torch tensor, host or device); gcount[G] GPU counts.
+        `sentinel`: cells at/above it are never proposed by the search (default 1e6)."""
+        if sentinel is not None:
+            check(self._lib.sb_set_sentinel(self._h, C.c_float(sentinel)))
+        if isinstance(T, torch.Tensor):
+            Tt = T.detach().to(torch.float32).contiguous()
+            J, S, G = Tt.shape
+            ptr = Tt.data_ptr()
+            keep = Tt
+        else:
+            Ta = np.ascontiguousarray(T, dtype=np.float32)
+            J, S, G = Ta.shape
+            ptr = Ta.ctypes.data
+            keep = Ta
+        if gcount is None:
+            gcount = list(range(1, G + 1))
+        gc = np.ascontiguousarray(gcount, dtype=np.uint8)
+        if gc.shape != (G,):
+            raise ValueError("gcount must have %d entries" % G)
+        check(self._lib.sb_set_table(self._h, C.c_void_p(ptr), C.c_void_p(gc.ctypes.data), J, S, G, 1))
+        del keep
+        self.J, self.S, self.G = int(J), int(S), int(G)
+        self.gcount = [int(x) for x in gc]
+        return self
+
+    def reduced_table(self) -> Tuple[np.ndarray, np.ndarray]:
+        tmin = np.empty((self.J, NSLOT), dtype=np.float32)
+        args = np.empty((self.J, NSLOT), dtype=np.uint8)
+        check(self._lib.sb_get_reduced(self._h, C.c_void_p(tmin.ctypes.data), C.c_void_p(args.ctypes.data)))
+        return tmin, args
+
+    @property
+    def prio_dtype(self):
+        return torch.uint8 if self.J <= 256 else torch.uint16
+
+    # ------------------------------------------------------------------ evaluation
+    def _check_cands(self, opt: torch.Tensor, prio: torch.Tensor, on_device: bool):
+        if opt.dtype != torch.uint8:
+            raise TypeError("opt must be uint8")
+        if prio.dtype != self.prio_dtype:
+            raise TypeError("prio must be %s for J=%d" % (self.prio_dtype, self.J))
+        if opt.dim() != 2 or prio.dim() != 2 or opt.shape != prio.shape:
+            raise ValueError("opt / prio must both be [B][J]")
+        if opt.shape[1] != self.J:
+            raise ValueError("candidates have %d jobs, table has %d" % (opt.shape[1], self.J))
+        if opt.stride(1) != 1 or prio.stride(1) != 1 or (opt.shape[0] > 1 and opt.stride(0) != prio.stride(0)):
+            raise ValueError("opt / prio rows must be contiguous with the same row stride")
+        if on_device and (opt.device != self.device or prio.device != self.device):
+            raise ValueError("candidates must live on %s" % self.device)
+        if not on_device and (opt.is_cuda or prio.is_cuda):
+            raise ValueError("host evaluation takes CPU tensors")
+        B = opt.shape[0]
+        stride = opt.stride(0) if B > 1 else max(opt.stride(0), self.J)
+        return B, stride
+
+    def eval(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False,
+             out: Optional[torch.Tensor] = None, best_key: Optional[torch.Tensor] = None, id_base: int = 0,
+             _force_generic: bool = False) -> torch.Tensor:
+        """Makespan of every candidate (device tensors).  Asynchronous on the handle's stream."""
+        B, stride = self._check_cands(opt, prio, True)
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32, device=self.device)
+        fl = _flags(integer_starts, reduced) | (_lib._FLAG_FORCE_GENERIC if _force_generic else 0)
+        kp = C.c_void_p(best_key.data_ptr()) if best_key is not None else None
+        check(self._lib.sb_eval(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride, fl,
+                                C.c_void_p(out.data_ptr()), kp, id_base & 0xffffffff))
+        return out
+
+    def last_eval_path(self) -> int:
+        return int(self._lib.sb_last_eval_path(self._h))
+
+    def validate(self, opt: torch.Tensor, prio: torch.Tensor, reduced: bool = False) -> int:
+        B, stride = self._check_cands(opt, prio, True)
+        bad = C.c_int64(0)
+        check(self._lib.sb_validate(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride,
+                                    _flags(False, reduced), C.byref(bad)))
+        return int(bad.value)
+
+    def eval_host(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same through HOST tensors (pinned for full PCIe speed): H2D + kernel + D2H, synchronous."""
+        B, stride = self._check_cands(opt, prio, False)
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32, pin_memory=True)
+        check(self._lib.sb_eval_host(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride,
+                                     _flags(integer_starts, reduced), C.c_void_p(out.data_ptr())))
+        return out
+
+    def eval_full(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False):
+        """(makespan[B], start[B][J], slotmask[B][J]) — slot-exact plan of every candidate."""
+        B, stride = self._check_cands(opt, prio, True)
+        mk = torch.empty(B, dtype=torch.float32, device=self.device)
+        start = torch.empty((B, self.J), dtype=torch.float32, device=self.device)
+        mask = torch.empty((B, self.J), dtype=torch.int32, device=self.device)
+        check(self._lib.sb_eval_full(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride,
+                                     _flags(integer_starts, reduced), C.c_void_p(mk.data_ptr()),
+                                     C.c_void_p(start.data_ptr()), C.c_void_p(mask.data_ptr())))
+        return mk, start, mask
+
+    def decode(self, opt: np.ndarray, prio: np.ndarray, integer_starts: bool = True, reduced: bool = False):
+        """One candidate (host arrays) -> dict(start, slotmask, strategy, gpus, makespan)."""
+        J = self.J
+        opt = np.ascontiguousarray(opt, dtype=np.uint8)
+        prio = np.ascontiguousarray(prio, dtype=np.uint8 if J <= 256 else np.uint16)
+        if opt.shape != (J,) or prio.shape != (J,):
+            raise ValueError("opt / prio must have J=%d entries" % J)
+        start = np.empty(J, dtype=np.float32)
+        mask = np.empty(J, dtype=np.uint32)
+        strat = np.empty(J, dtype=np.uint8)
+        gpus = np.empty(J, dtype=np.uint8)
+        mk = C.c_float(0)
+        check(self._lib.sb_decode(self._h, C.c_void_p(opt.ctypes.data), C.c_void_p(prio.ctypes.data),
+                                  _flags(integer_starts, reduced), C.c_void_p(start.ctypes.data),
+                                  C.c_void_p(mask.ctypes.data), C.c_void_p(strat.ctypes.data),
+                                  C.c_void_p(gpus.ctypes.data), C.byref(mk)))
+        return {"start": start, "slotmask": mask, "strategy": strat, "gpus": gpus, "makespan": float(mk.value)}
+
+    # ------------------------------------------------------------------ search
+    def search_init(self, chains: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
+                    reduced: bool = False, t_start: float = 0.02, t_end: float = 1e-4, total_rounds: int = 200,
+                    warm: Optional[Tuple[np.ndarray, np.ndarray]] = None):
+        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base, flags=_flags(integer_starts, reduced),
+                         t_start=t_start, t_end=t_end, total_rounds=total_rounds)
+        wo = wp = None
+        keep = None
+        if warm is not None:
+            o = np.ascontiguousarray(warm[0], dtype=np.uint8)
+            pr = np.ascontiguousarray(warm[1], dtype=np.uint8 if self.J <= 256 else np.uint16)
+            keep = (o, pr)
+            wo, wp = C.c_void_p(o.ctypes.data), C.c_void_p(pr.ctypes.data)
+        check(self._lib.sb_search_init(self._h, C.byref(p), wo, wp))
+        del keep
+        self._search_chains = chains
+        self._search_base = chain_base
+
+    def search_round(self, rounds: int = 1):
+        check(self._lib.sb_search_round(self._h, rounds))
+
+    def search_best_key(self) -> torch.Tensor:
+        """A 1-element int64 tensor aliasing the device-resident best key (makespan bits << 32 | id)."""
+        ptr = C.c_void_p()
+        check(self._lib.sb_search_best_key_ptr(self._h, C.byref(ptr)))
+        return _alias_int64(ptr.value, self.device)
+
+    def search_best(self):
+        J = self.J
+        opt = np.empty(J, dtype=np.uint8)
+        prio = np.empty(J, dtype=np.uint8 if J <= 256 else np.uint16)
+        mk = C.c_float(0)
+        key = C.c_uint64(0)
+        check(self._lib.sb_search_best(self._h, C.c_void_p(opt.ctypes.data), C.c_void_p(prio.ctypes.data),
+                                       C.byref(mk), C.byref(key)))
+        return opt, prio, float(mk.value), int(key.value)
+
+    def search_inject(self, opt: np.ndarray, prio: np.ndarray, copies: int = 1):
+        o = np.ascontiguousarray(opt, dtype=np.uint8)
+        p = np.ascontiguousarray(prio, dtype=np.uint8 if self.J <= 256 else np.uint16)
+        check(self._lib.sb_search_inject(self._h, C.c_void_p(o.ctypes.data), C.c_void_p(p.ctypes.data), copies))
+
+    def search_stats(self):
+        ev, rd = C.c_int64(0), C.c_int64(0)
+        check(self._lib.sb_search_stats(self._h, C.byref(ev), C.byref(rd)))
+        return int(ev.value), int(rd.value)
+
+
+class _CudaArrayView:
+    """Minimal __cuda_array_interface__ carrier so torch can alias library-owned device memory."""
+
+    def __init__(self, ptr, nbytes, typestr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2,
+                                         "strides": None}
+        self._nbytes = nbytes
+
+
+def _alias_int64(ptr: int, device: torch.device) -> torch.Tensor:
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArrayView(ptr, 8, "<i8", (1,)), device=device)
+
+
+# ---------------------------------------------------------------------- candidate helpers
+def padded_rows(B: int, J: int, dtype: torch.dtype, device, pinned: bool = False) -> torch.Tensor:
+    """A [B][J] view into storage whose rows are a multiple of 16 ELEMENTS apart, so that the byte
+    stride of both opt (u8) and prio (u8/u16) rows is 16-byte aligned (TMA bulk-copy path)."""
+    stride = (J + 15) // 16 * 16
+    if pinned:
+        buf = torch.zeros((B, stride), dtype=dtype, pin_memory=True)
+    else:
+        buf = torch.zeros((B, stride), dtype=dtype, device=device)
+    return buf[:, :J]
+
+
+def random_candidates(engine: Engine, B: int, valid: np.ndarray, seed: int = 0, gcount=None, device=None,
+                      pinned: bool = False):
+    """opt ~ U{valid cells of each job}, prio = random permutations (torch RNG on `device`)."""
+    J = engine.J
+    device = engine.device if device is None else torch.device(device)
+    gen_dev = device if device.type == "cuda" else torch.device("cpu")
+    g = torch.Generator(device=gen_dev)
+    g.manual_seed(seed)
+    _, S, G = valid.shape
+    gcount = engine.gcount if gcount is None else list(gcount)
+    opt = padded_rows(B, J, torch.uint8, device, pinned)
+    prio = padded_rows(B, J, engine.prio_dtype, device, pinned)
+    nmax = int(valid.reshape(J, -1).sum(axis=1).max())
+    cells = np.zeros((J, nmax), dtype=np.uint8)
+    ncell = np.zeros(J, dtype=np.int64)
+    for j in range(J):
+        c = [(s << 3) | (gcount[gi] - 1) for s in range(S) for gi in range(G) if valid[j, s, gi]]
+        cells[j, :len(c)] = c
+        ncell[j] = len(c)
+    cells_t = torch.from_numpy(cells).to(gen_dev)
+    ncell_t = torch.from_numpy(ncell).to(gen_dev)
+    chunk = max(1, min(B, (1 << 24) // max(J, 1)))
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        u = torch.rand((nb, J), generator=g, device=gen_dev)
+        pick = torch.minimum((u * ncell_t[None, :]).long(), ncell_t[None, :] - 1)
+        o = torch.gather(cells_t[None, :, :].expand(nb, -1, -1), 2, pick[:, :, None])[:, :, 0]
+        keys = torch.rand((nb, J), generator=g, device=gen_dev)
+        p = torch.argsort(keys, dim=1)
+        opt[b0:b0 + nb].copy_(o)
+        if engine.prio_dtype == torch.uint8:
+            prio[b0:b0 + nb].copy_(p.to(torch.uint8))
+        else:
+            prio[b0:b0 + nb].copy_(p.to(torch.int32).to(torch.uint16))
+    return opt, prio

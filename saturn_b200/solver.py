@@ -1,0 +1,287 @@
+"""`saturn.solver` drop-in: solve() and convert_into_comprehensible().
+
+Same call shapes, argument meaning and return structure as the reference
+(saturn/solver/milp.py:23 and :448, re-exported by saturn/solver/__init__.py:1-2), so
+`saturn.orchestrate` (orchestrator.py:21-23,55-61,69-75) and user code keep working:
+
+    sta, tga, bss, bna, boa, makespan = solve(task_list, presolved, gurobi=..., threads=...,
+                                               interval=..., timeout=...)
+    node_per_task, task_dependency_dict, start_times = convert_into_comprehensible(
+        task_list, bss, boa, tga, bna, sta)
+
+Instead of building the MILP of milp.py:96-319 and shelling out to Gurobi/CBC (milp.py:321-327),
+solve() uploads the (gpu_count, runtime) table the MILP would have been built from
+(milp.py:77-81), searches list-schedule candidates on the GPU (saturn_b200.search) and emits the
+winner in exactly the nested-list layout milp.py:330-352,445 returns.  `gurobi` and `threads` are
+accepted and ignored.  `timeout` bounds the wall-clock of the search, as it bounded the MILP.
+
+There is no CPU fallback: without the CUDA library / a GPU this raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from collections import defaultdict
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+NSLOT = 8            # GPUs per node, reference milp.py:62 (DEBUG = True -> 8 per node)
+REPLAN_THRESHOLD = 500.0   # milp.py:363
+
+
+class SolverError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------------------------------ inputs
+def gpu_time_tuples_of(task_list) -> List[List[tuple]]:
+    """[(gpu_count, runtime), ...] per task in dict-insertion order — milp.py:77-81."""
+    out = []
+    for task in task_list:
+        out.append([(g_count, strat.runtime) for g_count, strat in task.strategies.items()])
+    return out
+
+
+def _f32_ceil(x: float) -> np.float32:
+    """Smallest fp32 >= x, so that the device's (start + ceil(rt)) never under-estimates."""
+    v = np.float32(x)
+    if float(v) < x:
+        v = np.nextafter(v, np.float32(np.inf), dtype=np.float32)
+    return v
+
+
+def build_table(task_list):
+    """Task.strategies -> (T[J][1][8] fp32 by gpu_count column, usable[J][8], optindex[J][8]).
+
+    optindex[j][k-1] = position of the gpu_count-k option in task j's strategies dict (the index
+    `bss` is expressed in, milp.py:96-111,477-486), -1 if the task has no such option.
+    Options that cannot fit one node (gpu_count > 8, milp.py:62,209-227) are dropped; options whose
+    executor is None are the profiler's sentinels (PerformanceEvaluator.py:99,106) and are kept in
+    the table but never proposed unless a task has nothing else.
+    """
+    J = len(task_list)
+    T = np.full((J, 1, NSLOT), np.inf, dtype=np.float32)
+    optindex = np.full((J, NSLOT), -1, dtype=np.int64)
+    usable = np.zeros((J, NSLOT), dtype=bool)
+    for j, task in enumerate(task_list):
+        if len(task.strategies) == 0:
+            raise SolverError("task %r has no strategies; run the trial runner first" % getattr(task, "name", j))
+        for o, (g_count, strat) in enumerate(task.strategies.items()):
+            if not isinstance(g_count, (int, np.integer)) or g_count < 1 or g_count > NSLOT:
+                continue
+            rt = strat.runtime
+            if rt is None or not math.isfinite(rt) or rt < 0:
+                continue
+            v = _f32_ceil(float(rt))
+            if v < T[j, 0, g_count - 1]:
+                T[j, 0, g_count - 1] = v
+                optindex[j, g_count - 1] = o
+                usable[j, g_count - 1] = getattr(strat, "executor", True) is not None
+        if not np.isfinite(T[j]).any():
+            raise SolverError("task %r has no option that fits a node of %d GPUs" % (getattr(task, "name", j), NSLOT))
+    return T, usable, optindex
+
+
+# ------------------------------------------------------------------------------------------ outputs
+def plan_to_arrays(n_options: Sequence[int], opt_index: Sequence[int], start: Sequence[float],
+                   slotmask: Sequence[int], position: Sequence[int], nodes: int = 1):
+    """(start, GPU mask, chosen option, schedule position) per task -> the reference's arrays.
+
+    Layout and meaning follow milp.py:330-352: sta[N][G][J] start times (0 where the task does
+    not run), tga[J][N][G] occupancy, bss[J][S_t] one-hot option, bna[J][N] one-hot node,
+    boa[a][b] == 1 iff task a is ordered before task b (milp.py:292-319,510); the diagonal is
+    None exactly as the reference leaves it (those variables never enter a constraint).
+    All entries are plain Python floats.
+    """
+    J = len(n_options)
+    sta = [[[0.0] * J for _ in range(NSLOT)] for _ in range(nodes)]
+    tga = [[[0.0] * NSLOT for _ in range(nodes)] for _ in range(J)]
+    bss = [[0.0] * int(n_options[t]) for t in range(J)]
+    bna = [[1.0] + [0.0] * (nodes - 1) for _ in range(J)]
+    for t in range(J):
+        bss[t][int(opt_index[t])] = 1.0
+        m = int(slotmask[t])
+        s = float(start[t])
+        for g in range(NSLOT):
+            if (m >> g) & 1:
+                tga[t][0][g] = 1.0
+                sta[0][g][t] = s
+    pos = np.asarray(position)
+    before = (pos[:, None] < pos[None, :]).astype(np.float64)
+    boa = before.tolist()
+    for t in range(J):
+        boa[t][t] = None
+    return sta, tga, bss, bna, boa
+
+
+def candidate_from_arrays(task_list, presolved):
+    """Warm start: turn a previous plan (the `presolved` tuple) back into a candidate
+    (reduced opt bytes, priority order) — the role of setInitialValue at milp.py:103-104,151-155,197-202."""
+    if presolved is None:
+        return None
+    try:
+        sta, tga, bss, bna, boa, _mk = presolved
+        J = len(task_list)
+        if sta is None or len(tga) != J or len(bss) != J:
+            return None
+        opt = np.zeros(J, dtype=np.uint8)
+        starts = np.zeros(J)
+        for t, task in enumerate(task_list):
+            keys = list(task.strategies.keys())
+            if len(bss[t]) != len(keys):
+                return None
+            k = int(keys[int(np.argmax(bss[t]))])
+            if not 1 <= k <= NSLOT:
+                return None
+            opt[t] = k - 1
+            n = int(np.argmax(bna[t]))
+            gl = [g for g, v in enumerate(tga[t][n]) if v is not None and round(v) == 1]
+            starts[t] = sta[n][gl[0]][t] if gl else 0.0
+        order = np.argsort(starts, kind="stable")
+        return opt, order
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------ solve
+_ENGINE = None
+last_stats: dict = {}
+
+
+def _engine():
+    global _ENGINE
+    if _ENGINE is None:
+        from .engine import Engine
+        _ENGINE = Engine()
+    return _ENGINE
+
+
+def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count() or 4) // 4), interval=1000,
+          timeout=500, *, chains: Optional[int] = None, rounds: Optional[int] = None, seed: int = 0,
+          integer_starts: bool = True, engine=None):
+    """Drop-in for saturn.solver.solve (milp.py:23).
+
+    Returns (sta, tga, bss, bna, boa, makespan) — milp.py:445 — with a real float makespan
+    (the reference returns None on a cold start, milp.py:394-399; callers only thread it back in
+    as `presolved`).  Keyword-only extras tune the GPU search; environment overrides:
+    SATURN_B200_CHAINS, SATURN_B200_ROUNDS, SATURN_B200_BUDGET_S.
+    """
+    from .search import run_search
+    t_wall = time.perf_counter()
+    task_list = list(task_list)
+    J = len(task_list)
+    if J == 0:
+        return [[[] for _ in range(NSLOT)]], [], [], [], [], 0.0
+    eng = engine if engine is not None else _engine()
+    T, usable, optindex = build_table(task_list)
+    # sentinel cells (executor None) must never be proposed: they are removed from the device table
+    # unless the task has nothing else; every remaining finite cell is usable (sentinel = +inf)
+    Tdev = T.copy()
+    for j in range(J):
+        if usable[j].any():
+            Tdev[j, 0, ~usable[j]] = np.inf
+    eng.set_table(Tdev, list(range(1, NSLOT + 1)), sentinel=float("inf"))
+    if chains is None:
+        chains = int(os.environ.get("SATURN_B200_CHAINS", 1 << 16))
+    if rounds is None:
+        rounds = int(os.environ.get("SATURN_B200_ROUNDS", 300))
+    budget = float(os.environ.get("SATURN_B200_BUDGET_S", 20.0))
+    try:
+        budget = min(budget, float(timeout))
+    except (TypeError, ValueError):
+        pass
+    warm = candidate_from_arrays(task_list, presolved)
+    res = run_search(eng, chains=chains, rounds=rounds, seed=seed, integer_starts=integer_starts, reduced=True,
+                     time_budget_s=budget, patience=max(40, rounds // 4), warm=warm)
+    dec = eng.decode(res.opt, res.prio, integer_starts=integer_starts, reduced=True)
+    gpus = dec["gpus"].astype(np.int64)
+    chosen = optindex[np.arange(J), gpus - 1]
+    if (chosen < 0).any():
+        raise SolverError("search returned an option a task does not have")
+    position = np.empty(J, dtype=np.int64)
+    position[res.prio.astype(np.int64)] = np.arange(J)
+    n_options = [len(t.strategies) for t in task_list]
+    prop = plan_to_arrays(n_options, chosen, dec["start"], dec["slotmask"], position)
+    # the makespan the caller sees is recomputed in float64 from the emitted plan and the tasks'
+    # own (un-rounded) runtimes: max_t start_t + runtime_t  (milp.py:170-177)
+    rts = [list(t.strategies.values())[int(chosen[i])].runtime for i, t in enumerate(task_list)]
+    prop_makespan = max(float(dec["start"][i]) + float(rts[i]) for i in range(J))
+
+    global last_stats
+    last_stats = {"candidates": res.evaluated, "rounds": res.rounds, "search_wall_s": res.wall_s,
+                  "device_makespan": res.makespan, "makespan": prop_makespan, "J": J, "chains": chains,
+                  "total_wall_s": None, "adopted": True}
+
+    # ---- introspection hysteresis: the documented intent of milp.py:363-442
+    out = prop + (prop_makespan,)
+    if presolved is not None:
+        p_sta, p_tga, p_bss, p_bna, p_boa, saved = presolved
+        same_tasks = p_tga is not None and len(p_tga) == J
+        if saved is not None and same_tasks:
+            try:
+                itv = float(interval)
+            except (TypeError, ValueError):
+                itv = 1000.0
+            if not (prop_makespan < float(saved) - itv - REPLAN_THRESHOLD):
+                # keep the current plan, shifted by one interval (milp.py:429-442)
+                kept_sta = [[[max(float(v) - itv, 0.0) for v in g] for g in n] for n in p_sta]
+                out = (kept_sta, p_tga, p_bss, p_bna, p_boa, float(saved) - itv)
+                last_stats["adopted"] = False
+    last_stats["total_wall_s"] = time.perf_counter() - t_wall
+    return out
+
+
+# ------------------------------------------------------------------------------------------ decode
+def convert_into_comprehensible(task_list, bss, boa, tga, bna, sta):
+    """Drop-in for saturn.solver.convert_into_comprehensible (milp.py:448-513).
+
+    Returns (node_per_task: dict Task -> int, task_dependency_dict: defaultdict Task -> [Task],
+    start_time_per_task: list[float]) and, as the reference does, records the chosen option on
+    each task via task.select_strategy (milp.py:475-486).  The O(J^2 * G) Python triple loop of
+    milp.py:492-511 is replaced by bit-mask arithmetic; results are identical.
+    """
+    task_list = list(task_list)
+    J = len(task_list)
+    node_per_task = {}
+    nodes = np.zeros(J, dtype=np.int64)
+    for idx, task in enumerate(task_list):
+        n = np.argmax(bna[idx])
+        node_per_task[task] = n
+        nodes[idx] = int(n)
+    for idx, task in enumerate(task_list):
+        want = int(np.argmax(bss[idx]))
+        for ctr, strat in enumerate(task.strategies.values()):
+            if ctr == want:
+                task.select_strategy(strat)
+                break
+    masks = np.zeros(J, dtype=np.int64)
+    start_time_per_task = []
+    for idx in range(J):
+        row = tga[idx][int(nodes[idx])]
+        m = 0
+        first = -1
+        for g, v in enumerate(row):
+            if round(v) == 1:
+                m |= 1 << g
+                if first < 0:
+                    first = g
+        if first < 0:
+            raise SolverError("task %d occupies no GPU in tga" % idx)
+        masks[idx] = m
+        start_time_per_task.append(sta[int(nodes[idx])][first][idx])
+    task_dependency_dict = defaultdict(list)
+    if J > 1:
+        before = np.zeros((J, J), dtype=bool)      # before[p][t]: round(boa[p][t]) == 1
+        for p in range(J):
+            rowb = boa[p]
+            before[p] = [False if (v is None) else (round(v) == 1) for v in rowb]
+        np.fill_diagonal(before, False)
+        share = ((masks[:, None] & masks[None, :]) != 0) & (nodes[:, None] == nodes[None, :])
+        dep = before & share                       # dep[p][t]: p must finish before t launches
+        for idx in range(J):
+            ps = np.nonzero(dep[:, idx])[0]
+            if ps.size:
+                task_dependency_dict[task_list[idx]] = [task_list[int(p)] for p in ps]
+    return node_per_task, task_dependency_dict, start_time_per_task

@@ -1,0 +1,68 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+    p = os.path.join(ROOT, "tests", "golden", "milp_cases.json")
+    with open(p) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def engine():
+    import torch
+    from saturn_b200.engine import Engine
+    torch.cuda.set_device(0)
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+class DuckTask:
+    """The slice of Task the solver path touches (milp.py:77-81, 481-486)."""
+
+    def __init__(self, name, strategies, total_batches=100):
+        self.name = name
+        self.strategies = strategies
+        self.selected_strategy = None
+        self.total_batches = total_batches
+
+    def select_strategy(self, s):
+        self.selected_strategy = s
+
+
+def tasks_from_tuples(tuples, executor="exec"):
+    from saturn_b200 import Strategy
+    out = []
+    for t, tup in enumerate(tuples):
+        out.append(DuckTask("t%d" % t, {int(g): Strategy(executor, int(g), {}, float(rt)) for g, rt in tup}))
+    return out

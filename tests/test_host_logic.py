@@ -1,0 +1,170 @@
+"""CPU: host-side mirror of the reference interface (no GPU, no compute calls into the library)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DuckTask, tasks_from_tuples
+from oracle import ref_eval as R
+from saturn_b200 import HParams, Strategy, Task, Techniques, _lib
+from saturn_b200.orchestrator import forecast
+from saturn_b200.solver import (build_table, candidate_from_arrays, convert_into_comprehensible, gpu_time_tuples_of,
+                                plan_to_arrays)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "saturn_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(sb_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.SO_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert _lib.load().sb_abi_version() == 1
+
+
+def test_no_cpu_fallback_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.sb_create(0, None, ctypes.byref(h))
+    assert rc == -2 and not h.value                     # SB_ERR_CUDA
+    assert b"no CPU path" in lib.sb_last_error()
+    from saturn_b200.engine import Engine
+    with pytest.raises(_lib.SaturnB200Error):
+        Engine(0)
+    from saturn_b200 import solve
+    with pytest.raises(_lib.SaturnB200Error):
+        solve(tasks_from_tuples([[(1, 10.0)], [(2, 5.0)]]))
+
+
+def test_product_never_imports_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libref_eval|c_oracle|ref_eval\s*\(|ref_eval\.", re.M)
+    for top in ("saturn_b200", "saturn"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not pat.search(src), os.path.join(dirpath, f)
+
+
+def test_representations_behave_like_reference():
+    with pytest.raises(ValueError):
+        Strategy(None, 0)
+    with pytest.raises(ValueError):
+        Strategy(None, 2.0)
+    s = Strategy("ex", 4, {"a": 1}, 12.5)
+    assert (s.executor, s.gpu_apportionment, s.parameters, s.runtime) == ("ex", 4, {"a": 1}, 12.5)
+    assert str(s) == "Strategy(ex ({'a': 1}), 4G, 12.5s)"
+    with pytest.raises(ValueError):
+        HParams(0.1)
+    with pytest.raises(ValueError):
+        HParams(0.1, epochs=1, batch_count=3)
+    assert HParams(0.1, epochs=2).as_dict() == {"lr": 0.1, "epochs": 2, "batch_count": None}
+    assert [t.name for t in Techniques] == ["SPILLED", "PIPELINE", "FSDP", "MEGATRON"]
+
+
+def test_task_object(tmp_path):
+    t = Task(lambda: "model", lambda: list(range(10)), lambda a, b: 0.0, HParams(1e-3, epochs=3),
+             save_dir=str(tmp_path / "ckpt"))
+    assert t.epoch_length == 10 and t.total_batches == 30 and t.strategies == {} and t.selected_strategy is None
+    assert len(t.name) == 16 and os.path.isdir(t.save_dir)
+    t.reconfigure(13)
+    assert t.current_batch == 3 and next(t.get_iterator()) == 3 and next(t.get_fresh_iterator()) == 0
+    assert not t.has_ckpt() and t.get_model() == "model"
+    t2 = Task(lambda kw: kw, lambda: [0], None, HParams(1e-3, batch_count=7, width=5), save_dir=str(tmp_path))
+    assert t2.total_batches == 7 and t2.get_model() == {"width": 5}
+    with pytest.raises(ValueError):
+        Task(None, lambda: [0], None, HParams(1, epochs=1), hints={"is_transformer": True}, save_dir=str(tmp_path))
+    s = Strategy("e", 2, None, 5.0)
+    t.select_strategy(s)
+    assert t.selected_strategy is s
+    d = {t: 1}            # tasks are dict keys in the decoder's outputs (identity hash)
+    assert d[t] == 1
+
+
+def test_build_table_follows_dict_order_and_rounds_up():
+    tasks = tasks_from_tuples([[(2, 10.1), (1, 30.0)], [(8, 7.0)], [(4, 1.0000001), (16, 0.5)]])
+    assert gpu_time_tuples_of(tasks)[0] == [(2, 10.1), (1, 30.0)]
+    T, usable, optindex = build_table(tasks)
+    assert T.shape == (3, 1, 8) and T.dtype == np.float32
+    assert optindex[0, 1] == 0 and optindex[0, 0] == 1 and optindex[1, 7] == 0
+    assert optindex[2, 3] == 0 and (optindex[2] >= 0).sum() == 1           # 16 GPUs cannot fit a node
+    assert float(T[0, 0, 1]) >= 10.1 and float(T[2, 0, 3]) >= 1.0000001    # fp32 rounded UP
+    assert np.isinf(T[1, 0, 0])
+    tasks[0].strategies[1].executor = None
+    _, usable, _ = build_table(tasks)
+    assert not usable[0, 0] and usable[0, 1]
+
+
+def test_plan_arrays_satisfy_reference_constraints_and_decode():
+    tuples = [[(1, 100.5), (2, 60.2)], [(2, 50.0)], [(8, 10.0), (4, 18.0)]]
+    tasks = tasks_from_tuples(tuples)
+    # plan: t0 on 2 GPUs {0,1} at 0; t1 on {2,3} at 0; t2 on all 8 at 61
+    sta, tga, bss, bna, boa = plan_to_arrays([2, 1, 2], [1, 0, 0], [0.0, 0.0, 61.0], [0b11, 0b1100, 0xff], [0, 1, 2])
+    assert R.milp_constraints_hold(tuples, sta, tga, bss, bna, boa, 71.0) == []
+    assert R.milp_constraints_hold(tuples, sta, tga, bss, bna, boa, 70.0) != []      # makespan too small
+    assert all(isinstance(v, float) for n in sta for g in n for v in g)
+    assert boa[0][0] is None and boa[0][2] == 1.0 and boa[2][0] == 0.0
+    npt, tdd, st = convert_into_comprehensible(tasks, bss, boa, tga, bna, sta)
+    assert [npt[t] for t in tasks] == [0, 0, 0] and st == [0.0, 0.0, 61.0]
+    assert tdd[tasks[2]] == [tasks[0], tasks[1]] and tasks[0] not in tdd and tasks[1] not in tdd
+    assert tasks[0].selected_strategy.gpu_apportionment == 2 and tasks[2].selected_strategy.gpu_apportionment == 8
+    # an overlapping plan is rejected by the restated constraints
+    sta2, tga2, bss2, bna2, boa2 = plan_to_arrays([2, 1, 2], [1, 0, 0], [0.0, 0.0, 30.0], [0b11, 0b1100, 0xff],
+                                                  [0, 1, 2])
+    assert R.milp_constraints_hold(tuples, sta2, tga2, bss2, bna2, boa2, 100.0) != []
+    warm = candidate_from_arrays(tasks, (sta, tga, bss, bna, boa, 71.0))
+    assert list(warm[0]) == [1, 1, 7] and list(warm[1]) == [0, 1, 2]
+    assert candidate_from_arrays(tasks[:2], (sta, tga, bss, bna, boa, 71.0)) is None
+
+
+def test_decoder_matches_reference_decoder_on_reference_arrays(golden):
+    """convert_into_comprehensible on the arrays the reference MILP returned must reproduce what the
+    reference's own decoder (milp.py:448-513, run unmodified when the fixtures were generated) produced."""
+    n = 0
+    for rec in golden["cases"]:
+        if not rec["incumbent"]:
+            continue
+        tasks = tasks_from_tuples(rec["gpu_time_tuples"])
+        npt, tdd, st = convert_into_comprehensible(tasks, rec["bss"], rec["boa"], rec["tga"], rec["bna"], rec["sta"])
+        d = rec["decoded"]
+        assert [int(npt[t]) for t in tasks] == d["node_per_task"]
+        assert [float(s) for s in st] == d["start"]
+        idx = {t: i for i, t in enumerate(tasks)}
+        assert [sorted(idx[x] for x in tdd[t]) for t in tasks] == d["deps"]
+        assert [t.selected_strategy.gpu_apportionment for t in tasks] == d["selected_gpus"]
+        n += 1
+    assert n >= 10
+
+
+def test_forecast_restates_executor_semantics():
+    tasks = tasks_from_tuples([[(1, 1000.0), (2, 600.0)], [(2, 3000.0)], [(1, 100.0)]])
+    for t in tasks:
+        t.total_batches = 100
+        t.select_strategy(list(t.strategies.values())[0])
+    rel, btr, done = forecast(tasks, 500, [0.0, 100.0, 700.0])
+    assert rel == tasks[:2]
+    assert btr == [50.0, 13.0]            # 500 // 10 ; 400 // 30
+    assert done == set()
+    assert tasks[0].strategies[1].runtime == pytest.approx(500.0) and tasks[0].strategies[2].runtime == pytest.approx(300.0)
+    assert tasks[0].total_batches == 50 and tasks[1].total_batches == 87
+    assert tasks[2].total_batches == 100 and tasks[2].strategies[1].runtime == 100.0
+    rel, btr, done = forecast(tasks, 1000, [0.0, 0.0, 0.0])
+    assert tasks[0] in done and tasks[2] in done and tasks[1] not in done
+
+
+def test_alias_package_paths():
+    import saturn
+    import saturn.solver
+    import saturn.core.representations as rep
+    import saturn.executor
+    from saturn_b200 import solver
+    assert saturn.solver.solve is solver.solve and saturn.solver.convert_into_comprehensible is solver.convert_into_comprehensible
+    assert rep.Task is Task and rep.Strategy is Strategy and callable(saturn.orchestrate)
