@@ -27,9 +27,10 @@
  *   opt[b][j]    uint8: (s << 3) | (k - 1), k = GPU count of job j's option.
  *   prio[b][i]   uint8 (J <= 256) or uint16: job scheduled i-th; each row is a
  *                permutation of 0..J-1.
- *   rows of opt / prio are `row_stride` ELEMENTS apart (>= J).  When the byte
- *   stride is a multiple of 16 and the base pointer is 16-byte aligned the rows
- *   are fetched with TMA bulk copies, otherwise with plain loads.
+ *   rows of opt / prio are `row_stride` ELEMENTS apart (>= J).  Rows that are
+ *   32-byte aligned (base pointers and byte strides multiples of 32) take the
+ *   fast path (TMA bulk copies + 256-bit streaming loads); 16-byte aligned rows
+ *   use TMA bulk copies only; anything else is fetched with plain loads.
  *
  * Evaluation rule (one node, 8 GPU slots; reference milp.py:62,139-149,209-319)
  *   ready[0..8) = 0
@@ -103,7 +104,9 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
             unsigned flags, float* makespan_out, uint64_t* best_key, uint32_t id_base);
 
 /* which kernel the last sb_eval / sb_eval_host on this handle used:
- * 2 = tile kernel with TMA bulk row copies, 1 = tile kernel with plain row loads,
+ * 3 = tile kernel, opt rows by TMA bulk copy + prio rows streamed with 256-bit loads (rows 32-byte
+ *     aligned: the fast path), 2 = tile kernel with TMA bulk copies of both rows (16-byte aligned),
+ * 1 = tile kernel with plain row loads (unaligned rows),
  * 0 = generic kernel (rows read from global memory; J too large for shared-memory tiles) */
 int sb_last_eval_path(sb_handle* h);
 
@@ -155,8 +158,12 @@ int sb_search_round(sb_handle* h, int rounds);
 int sb_search_best_key_ptr(sb_handle* h, uint64_t** key_dev);
 /* copy the best candidate found so far to host buffers: opt u8 [J], prio u8/u16 [J] */
 int sb_search_best(sb_handle* h, uint8_t* opt, void* prio, float* makespan, uint64_t* key);
-/* overwrite the worst `copies` chains with the given candidate (host buffers) */
-int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int copies);
+/* overwrite chains [first_chain, first_chain + copies) — the last `copies` chains if first_chain < 0 —
+ * with the given candidate (host buffers), score them and fold them into the best key */
+int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t first_chain, int copies);
+/* tournament resampling: every chain continues from a random rival's candidate if the rival's
+ * current makespan is strictly better (keeps the population concentrated on good basins) */
+int sb_search_resample(sb_handle* h);
 /* candidates evaluated so far by this handle's searches */
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);
 

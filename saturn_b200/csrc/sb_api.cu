@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "sb_search.h"
@@ -262,7 +263,7 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
   c.out = makespan_out;
   c.best_key = reinterpret_cast<unsigned long long*>(best_key);
   c.id_base = id_base;
-  c.force_generic = (flags & 0x80000000u) ? 1 : 0;  // test hook: exercise the generic kernel
+  c.force_generic = (flags & 0x80000000u) ? 1 : 0;  // test hooks: 0x80000000 generic kernel, 0x40000000 no streaming
   CK(eval_launch(h->dev, c, h->stream, &h->last_path));
   return SB_OK;
 }
@@ -439,8 +440,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   d.chains = p->chains;
   d.chain_base = p->chain_base;
   d.seed = p->seed;
-  d.stride_o = (J + 15) & ~15;
-  d.stride_p = (J * pb + 15) & ~15;
+  d.stride_o = (J + 31) & ~31;  // 32-byte rows: TMA bulk copies for opt, 256-bit streaming loads for prio
   // make stride_p == stride_o * pb so that one element stride describes both (sb_eval contract)
   d.stride_p = d.stride_o * pb;
   const bool reduced = (p->flags & SB_FLAG_REDUCED) != 0;
@@ -533,7 +533,20 @@ int sb_search_best(sb_handle* h, uint8_t* opt, void* prio, float* makespan, uint
   return SB_OK;
 }
 
-int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int copies) {
+int sb_search_resample(sb_handle* h) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  CK(search_resample(s.d, s.rounds_done, h->stream));
+  // the resampled population was written to the proposal buffers: swap roles
+  std::swap(s.d.cur_o, s.d.prop_o);
+  std::swap(s.d.cur_p, s.d.prop_p);
+  std::swap(s.d.cur_mk, s.d.prop_mk);
+  return SB_OK;
+}
+
+int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t first_chain, int copies) {
   int rc = use_device(h);
   if (rc) return rc;
   SearchState& s = h->search;
@@ -541,7 +554,8 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int cop
   if (!opt || !prio) return fail(SB_ERR_ARG, "opt / prio is null");
   if (copies < 1) return SB_OK;
   if (copies > s.d.chains) copies = static_cast<int>(s.d.chains);
-  const long long first = s.d.chains - copies;
+  long long first = first_chain < 0 ? s.d.chains - copies : first_chain;
+  if (first + copies > s.d.chains) first = s.d.chains - copies;
   CK(cudaMemsetAsync(s.cand_o, 0, s.d.stride_o, h->stream));
   CK(cudaMemsetAsync(s.cand_p, 0, s.d.stride_p, h->stream));
   CK(cudaMemcpyAsync(s.cand_o, opt, s.d.J, cudaMemcpyHostToDevice, h->stream));

@@ -75,18 +75,36 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // entries are replaced by v = s + hold.  With sh[i] = f[i + k] (+inf past the end) the new sorted
 // state is  f'[i] = max(f[i], min(v, sh[i]))  — every surviving element below v moves down k
 // places, the k copies of v follow, larger elements stay.  sh is produced by a 3-stage barrel
-// shifter on the bits of km1 (24 selects), no dynamic register indexing and no divergence.
+// shifter on the bits of km1, no dynamic register indexing and no divergence.
+//
+// Pipe balance (ncu, profiles/r01_*): with all 24 barrel selects as FSEL the kernel saturates the
+// ALU pipe (96 % busy) while the FMA pipe idles at 4 %.  Stages 2 and 1 are therefore written as
+// in-place predicated moves expressed as `@p mad.lo dst, src, one, 0` with `one` a run-time 1
+// (a kernel argument, so ptxas cannot fold it back into SEL): they issue as predicated IMAD on
+// the FMA pipe.  Moving in ascending index order reads only not-yet-overwritten sources.
+__device__ __forceinline__ void pmov_fma(float& dst, float src, int bit, int one) {
+  int d = __float_as_int(dst);
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mad.lo.s32 %0, %1, %3, 0;\n\t}"
+      : "+r"(d)
+      : "r"(__float_as_int(src)), "r"(bit), "r"(one));
+  dst = __int_as_float(d);
+}
+
 template <bool kIntegerStarts>
-__device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1) {
+__device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1, int one) {
   const float INF = inf_f();
-  const bool b2 = (km1 & 4) != 0, b1 = (km1 & 2) != 0, b0 = (km1 & 1) != 0;
+  const bool b2 = (km1 & 4) != 0;
+  const int b1 = km1 & 2, b0 = km1 & 1;
+  // stage "shift by 4" (ALU pipe: FSEL / SEL)
   float x0 = b2 ? f[4] : f[0], x1 = b2 ? f[5] : f[1], x2 = b2 ? f[6] : f[2], x3 = b2 ? f[7] : f[3];
   float x4 = b2 ? INF : f[4], x5 = b2 ? INF : f[5], x6 = b2 ? INF : f[6], x7 = b2 ? INF : f[7];
-  float y0 = b1 ? x2 : x0, y1 = b1 ? x3 : x1, y2 = b1 ? x4 : x2, y3 = b1 ? x5 : x3;
-  float y4 = b1 ? x6 : x4, y5 = b1 ? x7 : x5, y6 = b1 ? INF : x6, y7 = b1 ? INF : x7;
-  float z0 = b0 ? y1 : y0, z1 = b0 ? y2 : y1, z2 = b0 ? y3 : y2, z3 = b0 ? y4 : y3;
-  float z4 = b0 ? y5 : y4, z5 = b0 ? y6 : y5, z6 = b0 ? y7 : y6, z7 = b0 ? INF : y7;
-  const float s = z0;  // = f[km1]
+  // stage "shift by 2" (FMA pipe: predicated IMAD, in place)
+  pmov_fma(x0, x2, b1, one); pmov_fma(x1, x3, b1, one); pmov_fma(x2, x4, b1, one); pmov_fma(x3, x5, b1, one);
+  pmov_fma(x4, x6, b1, one); pmov_fma(x5, x7, b1, one); pmov_fma(x6, INF, b1, one); pmov_fma(x7, INF, b1, one);
+  // stage "shift by 1"
+  pmov_fma(x0, x1, b0, one); pmov_fma(x1, x2, b0, one); pmov_fma(x2, x3, b0, one); pmov_fma(x3, x4, b0, one);
+  pmov_fma(x4, x5, b0, one); pmov_fma(x5, x6, b0, one); pmov_fma(x6, x7, b0, one); pmov_fma(x7, INF, b0, one);
+  const float s = x0;  // = f[km1]
   float v;
   if (kIntegerStarts) {
     // every entry of f is an integer here, so s is; the slot is usable again at s + ceil(rt)
@@ -95,13 +113,13 @@ __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int 
   } else {
     v = s + rt;
   }
-  f[0] = fmaxf(f[0], fminf(v, z1));
-  f[1] = fmaxf(f[1], fminf(v, z2));
-  f[2] = fmaxf(f[2], fminf(v, z3));
-  f[3] = fmaxf(f[3], fminf(v, z4));
-  f[4] = fmaxf(f[4], fminf(v, z5));
-  f[5] = fmaxf(f[5], fminf(v, z6));
-  f[6] = fmaxf(f[6], fminf(v, z7));
+  f[0] = fmaxf(f[0], fminf(v, x1));
+  f[1] = fmaxf(f[1], fminf(v, x2));
+  f[2] = fmaxf(f[2], fminf(v, x3));
+  f[3] = fmaxf(f[3], fminf(v, x4));
+  f[4] = fmaxf(f[4], fminf(v, x5));
+  f[5] = fmaxf(f[5], fminf(v, x6));
+  f[6] = fmaxf(f[6], fminf(v, x7));
   f[7] = fmaxf(f[7], v);
 }
 

@@ -8,10 +8,15 @@
 // Kernel shape (k_eval_tiles):
 //   * persistent grid, one CTA per SM, NW warps per CTA; the J x S x 8 runtime table is staged
 //     once per CTA into shared memory with TMA bulk copies (cp.async.bulk + mbarrier);
-//   * each warp owns a tile of 32 candidates: every lane fetches ITS candidate's opt row and
-//     prio row with one TMA bulk copy each into a padded shared-memory row (row stride = odd
-//     multiple of 16 B, so per-lane 128-bit reads are bank-conflict free), completion on a
-//     per-warp mbarrier — no CTA-wide barrier after start-up;
+//   * each warp owns a tile of 32 candidates: every lane fetches ITS candidate's opt row with one
+//     TMA bulk copy into a padded shared-memory row (the opt bytes are gathered by job id, so
+//     they must be resident), completion on a per-warp mbarrier — no CTA-wide barrier after
+//     start-up.  The prio row is consumed in order, so in the STREAM variant (rows 32-byte
+//     aligned) each lane streams it straight from HBM with 256-bit loads (one full 32-byte sector
+//     per lane, prefetched 32 steps ahead) and it never touches shared memory: 8.7 KB of smem per
+//     warp instead of 17.4 KB -> 16 resident warps per SM instead of 8 (ncu r01b: with 2 warps per
+//     scheduler 31 % of issue slots were lost to dependency waits).  Unaligned rows fall back to
+//     the non-STREAM variant (prio rows staged in shared memory, TMA or plain loads);
 //   * one candidate per LANE: the 8 slot ready-times live sorted in 8 registers and one
 //     scheduling step is ~45 predicated selects / min / max (sb_common.cuh: ls_step) — fp32
 //     min/max/add and byte indexing only, no tensor cores;
@@ -35,6 +40,7 @@ struct TileArgs {
   unsigned long long* best_key;
   uint32_t id_base;
   long long ntiles;
+  int one;  // run-time 1 (see pmov_fma)
 };
 
 template <int PB>
@@ -43,8 +49,20 @@ __device__ __forceinline__ int prio_at(const uint32_t (&w)[4], int t) {
   return (w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
 }
 
-template <int PB, bool INT>
-__global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
+struct PrioChunk {
+  uint32_t w[8];  // 32 bytes = 32 (u8) or 16 (u16) schedule positions
+};
+__device__ __forceinline__ PrioChunk ld_prio32(const uint8_t* p) {
+  PrioChunk c;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]),
+                 "=r"(c.w[7])
+               : "l"(p));
+  return c;
+}
+
+template <int PB, bool INT, bool STREAM>
+__global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const TileArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,7 +70,7 @@ __global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
   float* tab_s = reinterpret_cast<float*>(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((tab_bytes + 15u) & ~15u));
   uint8_t* tiles = reinterpret_cast<uint8_t*>(bars) + (((1 + nw) * 8 + 15) & ~15);
-  const uint32_t tile_bytes = 32u * (a.row_o + a.row_p);
+  const uint32_t tile_bytes = 32u * (a.row_o + (STREAM ? 0 : a.row_p));
   uint8_t* tile_o = tiles + static_cast<size_t>(warp) * tile_bytes;
   uint8_t* tile_p = tile_o + 32u * a.row_o;
   uint64_t* bar_tab = bars;
@@ -85,14 +103,71 @@ __global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
     __syncwarp();
     if (a.use_bulk) {
       fence_proxy_async();  // order the previous tile's generic-proxy reads before async writes
-      if (lane == 0) mbar_arrive_expect_tx(bar_w, static_cast<uint32_t>(nb) * (a.copy_o + a.copy_p));
+      if (lane == 0)
+        mbar_arrive_expect_tx(bar_w, static_cast<uint32_t>(nb) * (a.copy_o + (STREAM ? 0 : a.copy_p)));
       __syncwarp();
       if (active) {
         tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + (b0 + lane) * a.stride_o, a.copy_o, bar_w);
-        tma_bulk_g2s(tile_p + lane * a.row_p, a.prio + (b0 + lane) * a.stride_p, a.copy_p, bar_w);
+        if (!STREAM) tma_bulk_g2s(tile_p + lane * a.row_p, a.prio + (b0 + lane) * a.stride_p, a.copy_p, bar_w);
       }
+      PrioChunk q;
+      if (STREAM && active) q = ld_prio32(a.prio + (b0 + lane) * a.stride_p);  // overlaps the TMA wait
       mbar_wait(bar_w, phase);
       phase ^= 1;
+      if (STREAM) {
+        if (!tab_ready) {
+          mbar_wait(bar_tab, 0);
+          tab_ready = true;
+        }
+        float mk = 0.f;
+        if (active) {
+          const uint8_t* orow = tile_o + lane * a.row_o;
+          const uint8_t* pg = a.prio + (b0 + lane) * a.stride_p;
+          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          constexpr int STEPS = 32 / PB;  // schedule positions per 256-bit load
+          const int one = a.one;
+          const int SG = a.SG;
+          const int J = a.J;
+          const int nch = (J + STEPS - 1) / STEPS;
+          for (int c = 0; c < nch; ++c) {
+            PrioChunk nxt = q;
+            if (c + 1 < nch) nxt = ld_prio32(pg + (c + 1) * 32);
+            if ((c + 1) * STEPS <= J) {
+#pragma unroll
+              for (int t = 0; t < STEPS; ++t) {
+                const int j = PB == 1 ? (q.w[t >> 2] >> ((t & 3) * 8)) & 0xff : (q.w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
+                const int o = orow[j];
+                const float rt = tab_s[j * SG + o];
+                ls_step<INT>(f, mk, rt, o & 7, one);
+              }
+            } else {
+              const int rem = J - c * STEPS;
+#pragma unroll
+              for (int t = 0; t < STEPS; ++t) {
+                if (t < rem) {
+                  const int j = PB == 1 ? (q.w[t >> 2] >> ((t & 3) * 8)) & 0xff : (q.w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
+                  const int o = orow[j];
+                  const float rt = tab_s[j * SG + o];
+                  ls_step<INT>(f, mk, rt, o & 7, one);
+                }
+              }
+            }
+            q = nxt;
+          }
+          if (!INT) mk = f[7];
+          a.out[b0 + lane] = mk;
+        }
+        if (a.best_key != nullptr) {
+          const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
+          const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+          const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
+          if (lane == __ffs(who) - 1 && active) {
+            const unsigned long long key = pack_key(mk, a.id_base + static_cast<uint32_t>(b0 + lane));
+            if (key < *reinterpret_cast<volatile unsigned long long*>(a.best_key)) atomicMin(a.best_key, key);
+          }
+        }
+        continue;
+      }
     } else {
       for (int r = 0; r < nb; ++r) {
         const uint8_t* so = a.opt + (b0 + r) * a.stride_o;
@@ -113,6 +188,7 @@ __global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
       const uint4* prow = reinterpret_cast<const uint4*>(tile_p + lane * a.row_p);
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       constexpr int STEPS = 16 / PB;  // jobs per 128-bit prio read
+      const int one = a.one;
       const int nfull = a.J / STEPS;
       const int SG = a.SG;
       for (int c = 0; c < nfull; ++c) {
@@ -123,7 +199,7 @@ __global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
           const int j = prio_at<PB>(w, t);
           const int o = orow[j];
           const float rt = tab_s[j * SG + o];
-          ls_step<INT>(f, mk, rt, o & 7);
+          ls_step<INT>(f, mk, rt, o & 7, one);
         }
       }
       const int rem = a.J - nfull * STEPS;
@@ -136,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) k_eval_tiles(const TileArgs a) {
             const int j = prio_at<PB>(w, t);
             const int o = orow[j];
             const float rt = tab_s[j * SG + o];
-            ls_step<INT>(f, mk, rt, o & 7);
+            ls_step<INT>(f, mk, rt, o & 7, one);
           }
         }
       }
@@ -170,6 +246,7 @@ struct GenericArgs {
   unsigned long long* best_key;
   uint32_t id_base;
   int tab_in_smem;
+  int one;
 };
 
 template <int PB, bool INT>
@@ -193,11 +270,12 @@ __global__ void __launch_bounds__(128) k_eval_generic(const GenericArgs a) {
       const uint8_t* orow = a.opt + b * a.stride_o;
       const uint8_t* prow = a.prio + b * a.stride_p;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int one = a.one;
       for (int i = 0; i < a.J; ++i) {
         const int j = PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i];
         const int o = orow[j];
         const float rt = tab[j * a.SG + o];
-        ls_step<INT>(f, mk, rt, o & 7);
+        ls_step<INT>(f, mk, rt, o & 7, one);
       }
       if (!INT) mk = f[7];
       a.out[b] = mk;
@@ -316,23 +394,23 @@ static int round_row(int bytes) {
   return r16 * 16;
 }
 
-int plan_tiles(const Device& dev, int J, int SG, int pb, TilePlan* tp) {
+int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, TilePlan* tp) {
   tp->row_o = round_row(J);
   tp->row_p = round_row(J * pb);
   tp->copy_o = (J + 15) & ~15;
   tp->copy_p = (J * pb + 15) & ~15;
   const size_t tab_bytes = (static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15);
-  const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + tp->row_p);
-  int nw = 8;
+  const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + (stream ? 0 : tp->row_p));
+  int nw = stream ? 16 : 8;
   while (nw > 0 && tab_bytes + 16 * ((1 + nw + 1) / 2) + nw * per_warp > dev.smem_optin) --nw;
   tp->warps = nw;
   tp->smem = tab_bytes + (((1 + nw) * 8 + 15) & ~15) + nw * per_warp;
   return nw;
 }
 
-template <int PB, bool INT>
+template <int PB, bool INT, bool STREAM>
 static cudaError_t launch_tiles(const Device& dev, const TileArgs& a, const TilePlan& tp, cudaStream_t st) {
-  auto kern = k_eval_tiles<PB, INT>;
+  auto kern = k_eval_tiles<PB, INT, STREAM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
   if (e != cudaSuccess) return e;
   long long ctas = (a.ntiles + tp.warps - 1) / tp.warps;
@@ -366,26 +444,41 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
   if (c.B <= 0) return cudaSuccess;
   const int pb = c.J <= 256 ? 1 : 2;
   const bool ints = (c.flags & SB_FLAG_INTEGER_STARTS) != 0;
+  const bool bulk_ok = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0);
+  const bool stream_ok = bulk_ok && (c.stride_p % 32 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 32 == 0) &&
+                         !(c.flags & 0x40000000u);
   TilePlan tp;
-  int nw = c.force_generic ? 0 : plan_tiles(dev, c.J, c.SG, pb, &tp);
+  int nw = 0;
+  bool stream = false;
+  if (!c.force_generic) {
+    if (stream_ok) {
+      nw = plan_tiles(dev, c.J, c.SG, pb, true, &tp);
+      stream = nw >= 2 && c.stride_o >= tp.copy_o && c.stride_p >= ((c.J * pb + 31) & ~31);
+    }
+    if (!stream) nw = plan_tiles(dev, c.J, c.SG, pb, false, &tp);
+  }
   if (nw >= 2) {
     TileArgs a;
     a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
     a.stride_o = c.stride_o; a.stride_p = c.stride_p;
     a.row_o = tp.row_o; a.row_p = tp.row_p; a.copy_o = tp.copy_o; a.copy_p = tp.copy_p;
-    a.use_bulk = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
-                 (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0) &&
-                 (c.stride_o >= tp.copy_o) && (c.stride_p >= tp.copy_p);
+    a.use_bulk = stream || (bulk_ok && (c.stride_o >= tp.copy_o) && (c.stride_p >= tp.copy_p));
     a.out = c.out; a.best_key = c.best_key; a.id_base = c.id_base;
     a.ntiles = (c.B + 31) / 32;
-    if (path_used) *path_used = a.use_bulk ? 2 : 1;
-    if (pb == 1) return ints ? launch_tiles<1, true>(dev, a, tp, st) : launch_tiles<1, false>(dev, a, tp, st);
-    return ints ? launch_tiles<2, true>(dev, a, tp, st) : launch_tiles<2, false>(dev, a, tp, st);
+    a.one = 1;
+    if (path_used) *path_used = stream ? 3 : (a.use_bulk ? 2 : 1);
+    if (stream) {
+      if (pb == 1) return ints ? launch_tiles<1, true, true>(dev, a, tp, st) : launch_tiles<1, false, true>(dev, a, tp, st);
+      return ints ? launch_tiles<2, true, true>(dev, a, tp, st) : launch_tiles<2, false, true>(dev, a, tp, st);
+    }
+    if (pb == 1) return ints ? launch_tiles<1, true, false>(dev, a, tp, st) : launch_tiles<1, false, false>(dev, a, tp, st);
+    return ints ? launch_tiles<2, true, false>(dev, a, tp, st) : launch_tiles<2, false, false>(dev, a, tp, st);
   }
   GenericArgs g;
   g.tab = c.tab; g.J = c.J; g.SG = c.SG; g.opt = c.opt; g.prio = c.prio; g.B = c.B;
   g.stride_o = c.stride_o; g.stride_p = c.stride_p; g.out = c.out; g.best_key = c.best_key;
-  g.id_base = c.id_base; g.tab_in_smem = 0;
+  g.id_base = c.id_base; g.tab_in_smem = 0; g.one = 1;
   if (path_used) *path_used = 0;
   if (pb == 1) return ints ? launch_generic<1, true>(dev, g, st) : launch_generic<1, false>(dev, g, st);
   return ints ? launch_generic<2, true>(dev, g, st) : launch_generic<2, false>(dev, g, st);

@@ -33,7 +33,7 @@ struct EvalCall {
   int force_generic = 0;
 };
 
-int plan_tiles(const Device& dev, int J, int SG, int pb, TilePlan* tp);
+int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, TilePlan* tp);
 cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used);
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st);
 cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st);

@@ -157,6 +157,24 @@ __global__ void k_inject(SearchDev s, const uint8_t* cand_o, const uint8_t* cand
   copy_row16(s.cur_p + c * s.stride_p, cand_p, static_cast<int>(s.stride_p), lane);
 }
 
+// ---- tournament resampling ("go with the winners"): every chain draws a random rival and, if the
+// rival's current makespan is strictly better, continues from a copy of the rival's candidate.
+// Two passes through the proposal buffers (then the host swaps the buffer roles), so no chain is
+// read while it is being overwritten.  Warp per chain.
+template <int PB>
+__global__ void k_resample(SearchDev s, int round) {
+  const int lane = threadIdx.x & 31;
+  const long long c = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (c >= s.chains) return;
+  const uint64_t gid = s.chain_base + static_cast<uint64_t>(c);
+  const uint64_t r = rng_u64(s.seed ^ 0x7e57a11ull, gid, static_cast<uint64_t>(round));
+  const long long d = bounded(r, static_cast<uint32_t>(s.chains));
+  const long long src = (s.cur_mk[d] < s.cur_mk[c]) ? d : c;
+  copy_row16(s.prop_o + c * s.stride_o, s.cur_o + src * s.stride_o, static_cast<int>(s.stride_o), lane);
+  copy_row16(s.prop_p + c * s.stride_p, s.cur_p + src * s.stride_p, static_cast<int>(s.stride_p), lane);
+  if (lane == 0) s.prop_mk[c] = s.cur_mk[src];
+}
+
 // ------------------------------------------------------------------------------------------ host
 static int warp_grid(long long warps, int threads) {
   long long blocks = (warps * 32 + threads - 1) / threads;
@@ -187,6 +205,13 @@ cudaError_t search_keep_best(const SearchDev& s, bool from_cur, cudaStream_t st)
 cudaError_t search_accept(const SearchDev& s, int round, float temperature, cudaStream_t st) {
   const int threads = 256;
   k_accept<<<warp_grid(s.chains, threads), threads, 0, st>>>(s, round, temperature);
+  return cudaGetLastError();
+}
+
+cudaError_t search_resample(const SearchDev& s, int round, cudaStream_t st) {
+  const int threads = 256;
+  if (s.pb == 1) k_resample<1><<<warp_grid(s.chains, threads), threads, 0, st>>>(s, round);
+  else k_resample<2><<<warp_grid(s.chains, threads), threads, 0, st>>>(s, round);
   return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@ cudaError_t search_init_population(const SearchDev& s, cudaStream_t st);
 cudaError_t search_propose(const SearchDev& s, int round, cudaStream_t st);
 cudaError_t search_keep_best(const SearchDev& s, bool from_cur, cudaStream_t st);
 cudaError_t search_accept(const SearchDev& s, int round, float temperature, cudaStream_t st);
+cudaError_t search_resample(const SearchDev& s, int round, cudaStream_t st);
 cudaError_t search_inject(const SearchDev& s, const uint8_t* cand_o, const uint8_t* cand_p, long long first,
                           int copies, cudaStream_t st);
 

@@ -119,12 +119,13 @@ class Engine:
 
     def eval(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False,
              out: Optional[torch.Tensor] = None, best_key: Optional[torch.Tensor] = None, id_base: int = 0,
-             _force_generic: bool = False) -> torch.Tensor:
+             _force_generic: bool = False, _no_stream: bool = False) -> torch.Tensor:
         """Makespan of every candidate (device tensors).  Asynchronous on the handle's stream."""
         B, stride = self._check_cands(opt, prio, True)
         if out is None:
             out = torch.empty(B, dtype=torch.float32, device=self.device)
-        fl = _flags(integer_starts, reduced) | (_lib._FLAG_FORCE_GENERIC if _force_generic else 0)
+        fl = _flags(integer_starts, reduced) | (_lib._FLAG_FORCE_GENERIC if _force_generic else 0) | (
+            0x40000000 if _no_stream else 0)
         kp = C.c_void_p(best_key.data_ptr()) if best_key is not None else None
         check(self._lib.sb_eval(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride, fl,
                                 C.c_void_p(out.data_ptr()), kp, id_base & 0xffffffff))
@@ -216,10 +217,14 @@ class Engine:
                                        C.byref(mk), C.byref(key)))
         return opt, prio, float(mk.value), int(key.value)
 
-    def search_inject(self, opt: np.ndarray, prio: np.ndarray, copies: int = 1):
+    def search_inject(self, opt: np.ndarray, prio: np.ndarray, copies: int = 1, first: int = -1):
         o = np.ascontiguousarray(opt, dtype=np.uint8)
         p = np.ascontiguousarray(prio, dtype=np.uint8 if self.J <= 256 else np.uint16)
-        check(self._lib.sb_search_inject(self._h, C.c_void_p(o.ctypes.data), C.c_void_p(p.ctypes.data), copies))
+        check(self._lib.sb_search_inject(self._h, C.c_void_p(o.ctypes.data), C.c_void_p(p.ctypes.data), first,
+                                         copies))
+
+    def search_resample(self):
+        check(self._lib.sb_search_resample(self._h))
 
     def search_stats(self):
         ev, rd = C.c_int64(0), C.c_int64(0)
@@ -243,9 +248,9 @@ def _alias_int64(ptr: int, device: torch.device) -> torch.Tensor:
 
 # ---------------------------------------------------------------------- candidate helpers
 def padded_rows(B: int, J: int, dtype: torch.dtype, device, pinned: bool = False) -> torch.Tensor:
-    """A [B][J] view into storage whose rows are a multiple of 16 ELEMENTS apart, so that the byte
-    stride of both opt (u8) and prio (u8/u16) rows is 16-byte aligned (TMA bulk-copy path)."""
-    stride = (J + 15) // 16 * 16
+    """A [B][J] view into storage whose rows are a multiple of 32 ELEMENTS apart, so that the byte
+    stride of both opt (u8) and prio (u8/u16) rows is 32-byte aligned (the kernel's fast path)."""
+    stride = (J + 31) // 32 * 32
     if pinned:
         buf = torch.zeros((B, stride), dtype=dtype, pin_memory=True)
     else:

@@ -63,9 +63,9 @@ def lpt_seeds(tmin: np.ndarray, sentinel: float = 1.0e6):
 
 def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: int = 0,
                integer_starts: bool = True, reduced: bool = False, time_budget_s: Optional[float] = None,
-               patience: Optional[int] = None, t_start: float = 0.02, t_end: float = 1e-4,
+               patience: Optional[int] = None, t_start: float = 2e-3, t_end: float = 1e-5,
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
-               target_makespan: Optional[float] = None, reseed_every: int = 0,
+               target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 8,
                record_history: bool = False, heuristic_seeds: bool = True) -> SearchResult:
     """Run the search on `engine` (table already set).  Returns the best candidate found by any rank."""
     dist = _dist() if use_dist else None
@@ -76,11 +76,15 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     t0 = time.perf_counter()
     engine.search_init(chains, seed=seed, chain_base=rank * chains, integer_starts=integer_starts,
                        reduced=reduced, t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1), warm=warm)
-    if heuristic_seeds and rank == 0:
+    if heuristic_seeds:
+        # every rank plants the longest-processing-time seeds in an eighth of its population each;
+        # the rest stays random (diversity), tournament resampling then concentrates the population
         tmin, args = engine.reduced_table()
-        for col, order in lpt_seeds(tmin):
+        per = max(1, chains // 8)
+        for i, (col, order) in enumerate(lpt_seeds(tmin)):
             opt = col if reduced else ((args[np.arange(J), col].astype(np.uint8) << 3) | col)
-            engine.search_inject(opt.astype(np.uint8), order.astype(pdt), copies=1)
+            first = min(i * per, max(0, chains - per))
+            engine.search_inject(opt.astype(np.uint8), order.astype(pdt), copies=min(per, chains), first=first)
     local_key = engine.search_best_key()          # aliases device memory
     gkey = torch.empty(1, dtype=torch.int64, device=engine.device)
     history: List[Tuple[float, int, float]] = []
@@ -125,9 +129,11 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
             want_stop = bool(stop.item())
         if want_stop:
             break
+        if resample_every and (r + 1) % resample_every == 0 and r + 1 < rounds:
+            engine.search_resample()
         if reseed_every and (r + 1) % reseed_every == 0 and r + 1 < rounds:
             opt, prio = _gather_best(engine, best_seen, chains, dist, rank)
-            engine.search_inject(opt, prio, copies=max(1, chains // 64))
+            engine.search_inject(opt, prio, copies=max(1, chains // 64), first=-1)
     opt, prio = _gather_best(engine, best_seen, chains, dist, rank)
     ev, _ = engine.search_stats()
     total_ev = ev

@@ -48,10 +48,15 @@ class FakeEngine:
         self._fold(self.mk, chain_base)
         self.evaluated = chains
 
-    def search_inject(self, opt, prio, copies=1):
+    def search_resample(self):
+        pass
+
+    def search_inject(self, opt, prio, copies=1, first=-1):
         self._inj = (np.asarray(opt).copy(), np.asarray(prio).copy())
         mk = self._score(opt[None, :], prio[None, :])
-        key = (int(np.float32(mk[0]).view(np.uint32)) << 32) | (self.base + self.chains - copies)
+        if first < 0:
+            first = self.chains - copies
+        key = (int(np.float32(mk[0]).view(np.uint32)) << 32) | (self.base + first)
         if key < int(self._key.item()):
             self._key.fill_(key)
             self._best = self._inj
@@ -88,7 +93,7 @@ def _worker(rank, world, port, q):
         T, valid = R.synth_table(12, 2, 8, seed=1)
         tab = R.canon_table(T, range(1, 9))
         eng = FakeEngine(tab, valid)
-        res = run_search(eng, chains=16, rounds=5, seed=3, use_dist=True, heuristic_seeds=(rank == 0))
+        res = run_search(eng, chains=16, rounds=5, seed=3, use_dist=True)
         # every rank ends with the SAME incumbent and it evaluates to the agreed makespan
         mk = float(R.list_schedule(tab, res.opt, res.prio, True, np.float32)[0])
         local_best = key_makespan(int(eng.search_best_key().item()))

@@ -36,7 +36,7 @@ def test_makespan_bit_exact_vs_oracle_fp32(engine, J, S, G, B, ints):
     assert engine.validate(opt, prio) == 0
     mk = engine.eval(opt, prio, integer_starts=ints)
     torch.cuda.synchronize()
-    assert engine.last_eval_path() == 2          # tile kernel, TMA row copies
+    assert engine.last_eval_path() == 3          # tile kernel: TMA opt rows + streamed prio rows
     ref = c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy(), ints, np.float32, threads=8)
     assert np.array_equal(mk.cpu().numpy(), ref)
     ref64 = c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy(), ints, np.float64, threads=8)
@@ -59,12 +59,15 @@ def test_slot_indices_and_starts_bit_exact(engine, J, S, G, B, ints):
 
 
 def test_all_kernel_paths_agree(engine):
-    """TMA tile kernel, plain-load tile kernel (unaligned rows) and the generic kernel are three
-    independent data paths over the same step function."""
+    """Streaming tile kernel, TMA-only tile kernel, plain-load tile kernel (unaligned rows) and the
+    generic kernel are four independent data paths over the same step function."""
     J, S, G, B = 100, 4, 8, 3001
     T, valid, tab, opt, prio = _setup(engine, J, S, G, B, seed=5)
     a = engine.eval(opt, prio)
+    assert engine.last_eval_path() == 3
+    a2 = engine.eval(opt, prio, _no_stream=True)
     assert engine.last_eval_path() == 2
+    assert torch.equal(a, a2)
     opt_u = opt.contiguous()              # row stride J = 100 bytes: not 16-byte aligned
     prio_u = prio.contiguous()
     b = engine.eval(opt_u, prio_u)
@@ -86,6 +89,7 @@ def test_u16_priorities(engine, J, S):
     assert np.array_equal(mk.cpu().numpy(), ref)
     g = engine.eval(opt, prio, _force_generic=True)
     assert torch.equal(mk, g)
+    assert torch.equal(mk, engine.eval(opt, prio, _no_stream=True))
 
 
 def test_reduced_table_matches_profiler_reduction(engine):
@@ -127,12 +131,14 @@ def test_gcount_mapping_and_absent_options(engine):
     mk = engine.eval(opt, prio)
     ref = c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy(), True, np.float32)
     assert np.array_equal(mk.cpu().numpy(), ref)
-    opt2 = opt.clone()
+    opt2 = padded_rows(500, J, torch.uint8, engine.device)
+    opt2.copy_(opt)
     opt2[:, 3] = 2                      # 3 GPUs: no such column
     mk2 = engine.eval(opt2, prio)
     assert torch.isinf(mk2).all()
     assert engine.validate(opt2, prio) == 500
-    prio2 = prio.clone()
+    prio2 = padded_rows(500, J, torch.uint8, engine.device)
+    prio2.copy_(prio)
     prio2[7, 0] = prio2[7, 1]           # not a permutation
     assert engine.validate(opt, prio2) == 1
 

@@ -168,3 +168,11 @@ def test_alias_package_paths():
     from saturn_b200 import solver
     assert saturn.solver.solve is solver.solve and saturn.solver.convert_into_comprehensible is solver.convert_into_comprehensible
     assert rep.Task is Task and rep.Strategy is Strategy and callable(saturn.orchestrate)
+
+
+def test_product_and_oracle_generate_the_same_workload():
+    from saturn_b200.synth import synth_table
+    for (J, S, G, seed) in [(4, 2, 2, 0), (64, 6, 8, 0), (256, 8, 8, 0)]:
+        a, va = synth_table(J, S, G, seed)
+        b, vb = R.synth_table(J, S, G, seed)
+        assert np.array_equal(a, b) and np.array_equal(va, vb)
