@@ -143,11 +143,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)      # torchrun pins it to 1; the CPU arm may use every core
     from oracle import c_oracle, ref_eval as R
     threads = c_oracle.max_threads()
     T, valid = R.synth_table(J, S, G, seed=0)
     tab = R.canon_table(T, range(1, G + 1))
-    per_step = 40000
+    per_step = 200000
     opt, prio = R.synth_candidates(J, per_step, valid, seed=1)
     for _ in range(args.warmup):
         c_oracle.evaluate(tab, opt, prio, True, np.float32, threads=threads)

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsaturn_b200.so")
+SO_PATH = os.environ.get("SATURN_B200_LIB") or os.path.join(_HERE, "libsaturn_b200.so")
 
 FLAG_INTEGER_STARTS = 1
 FLAG_REDUCED = 2

@@ -90,20 +90,55 @@ __device__ __forceinline__ void pmov_fma(float& dst, float src, int bit, int one
   dst = __int_as_float(d);
 }
 
+// dst = +inf under the predicate, as `@p add.f32 dst, dst, +inf` (x + inf = inf for every x >= 0):
+// it depends on dst, so ptxas cannot hoist it into a SEL of a loop-invariant; it issues as a
+// predicated FADD on the FMA pipe.
+__device__ __forceinline__ void pinf_fma(float& dst, int bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p add.f32 %0, %0, 0f7F800000;\n\t}" : "+f"(dst) : "r"(bit));
+}
+
+#ifndef SB_STAGE4_FMA
+#define SB_STAGE4_FMA 2
+#endif
+__device__ __forceinline__ float copy_fadd(float x, float negzero) {
+  float r;
+  asm("add.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(negzero));
+  return r;
+}
+
 template <bool kIntegerStarts>
 __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1, int one) {
   const float INF = inf_f();
-  const bool b2 = (km1 & 4) != 0;
   const int b1 = km1 & 2, b0 = km1 & 1;
+#if SB_STAGE4_FMA == 1
+  // stage "shift by 4" on the FMA pipe as well: copy (an FADD of -0.0 the compiler cannot fold:
+  // the addend is `one`-derived) + in-place predicated IMAD
+  const int b2i = km1 & 4;
+  const float nz = __int_as_float(one << 31);  // -0.0f at run time
+  float x0 = copy_fadd(f[0], nz), x1 = copy_fadd(f[1], nz), x2 = copy_fadd(f[2], nz), x3 = copy_fadd(f[3], nz);
+  float x4 = copy_fadd(f[4], nz), x5 = copy_fadd(f[5], nz), x6 = copy_fadd(f[6], nz), x7 = copy_fadd(f[7], nz);
+  pmov_fma(x0, f[4], b2i, one); pmov_fma(x1, f[5], b2i, one); pmov_fma(x2, f[6], b2i, one); pmov_fma(x3, f[7], b2i, one);
+  pinf_fma(x4, b2i); pinf_fma(x5, b2i); pinf_fma(x6, b2i); pinf_fma(x7, b2i);
+#else
   // stage "shift by 4" (ALU pipe: FSEL / SEL)
+  const bool b2 = (km1 & 4) != 0;
   float x0 = b2 ? f[4] : f[0], x1 = b2 ? f[5] : f[1], x2 = b2 ? f[6] : f[2], x3 = b2 ? f[7] : f[3];
+#if SB_STAGE4_FMA == 0
   float x4 = b2 ? INF : f[4], x5 = b2 ? INF : f[5], x6 = b2 ? INF : f[6], x7 = b2 ? INF : f[7];
+#else
+  // upper half: copy on the FMA pipe (FADD of a run-time -0.0) + predicated FADD of +inf
+  const int b2i = km1 & 4;
+  const float nz = __int_as_float(one << 31);
+  float x4 = copy_fadd(f[4], nz), x5 = copy_fadd(f[5], nz), x6 = copy_fadd(f[6], nz), x7 = copy_fadd(f[7], nz);
+  pinf_fma(x4, b2i); pinf_fma(x5, b2i); pinf_fma(x6, b2i); pinf_fma(x7, b2i);
+#endif
+#endif
   // stage "shift by 2" (FMA pipe: predicated IMAD, in place)
   pmov_fma(x0, x2, b1, one); pmov_fma(x1, x3, b1, one); pmov_fma(x2, x4, b1, one); pmov_fma(x3, x5, b1, one);
-  pmov_fma(x4, x6, b1, one); pmov_fma(x5, x7, b1, one); pmov_fma(x6, INF, b1, one); pmov_fma(x7, INF, b1, one);
+  pmov_fma(x4, x6, b1, one); pmov_fma(x5, x7, b1, one); pinf_fma(x6, b1); pinf_fma(x7, b1);
   // stage "shift by 1"
   pmov_fma(x0, x1, b0, one); pmov_fma(x1, x2, b0, one); pmov_fma(x2, x3, b0, one); pmov_fma(x3, x4, b0, one);
-  pmov_fma(x4, x5, b0, one); pmov_fma(x5, x6, b0, one); pmov_fma(x6, x7, b0, one); pmov_fma(x7, INF, b0, one);
+  pmov_fma(x4, x5, b0, one); pmov_fma(x5, x6, b0, one); pmov_fma(x6, x7, b0, one); pinf_fma(x7, b0);
   const float s = x0;  // = f[km1]
   float v;
   if (kIntegerStarts) {
