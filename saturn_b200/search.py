@@ -63,9 +63,9 @@ def lpt_seeds(tmin: np.ndarray, sentinel: float = 1.0e6):
 
 def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: int = 0,
                integer_starts: bool = True, reduced: bool = False, time_budget_s: Optional[float] = None,
-               patience: Optional[int] = None, t_start: float = 2e-3, t_end: float = 1e-5,
+               patience: Optional[int] = None, t_start: float = 5e-4, t_end: float = 1e-6,
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
-               target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 8,
+               target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 4,
                record_history: bool = False, heuristic_seeds: bool = True) -> SearchResult:
     """Run the search on `engine` (table already set).  Returns the best candidate found by any rank."""
     dist = _dist() if use_dist else None

@@ -160,13 +160,20 @@ def _engine():
 
 def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count() or 4) // 4), interval=1000,
           timeout=500, *, chains: Optional[int] = None, rounds: Optional[int] = None, seed: int = 0,
-          integer_starts: bool = True, engine=None):
+          integer_starts: bool = True, engine=None, hysteresis: Optional[bool] = None):
     """Drop-in for saturn.solver.solve (milp.py:23).
 
     Returns (sta, tga, bss, bna, boa, makespan) — milp.py:445 — with a real float makespan
     (the reference returns None on a cold start, milp.py:394-399; callers only thread it back in
     as `presolved`).  Keyword-only extras tune the GPU search; environment overrides:
-    SATURN_B200_CHAINS, SATURN_B200_ROUNDS, SATURN_B200_BUDGET_S.
+    SATURN_B200_CHAINS, SATURN_B200_ROUNDS, SATURN_B200_BUDGET_S, SATURN_B200_HYSTERESIS.
+
+    Re-planning policy.  As shipped, the reference ALWAYS adopts the fresh plan: its comparator
+    (milp.py:383-442) keys on `saved_makespan`, which stays None from the cold start on
+    (milp.py:394-399 never assigns it), so the swap / keep branches are unreachable.
+    That observable behaviour is the default here.  `hysteresis=True` (or SATURN_B200_HYSTERESIS=1)
+    enables the documented intent instead: keep the current plan, shifted by one interval, unless
+    the new one is better by more than interval + 500 s (milp.py:363,377,429-442).
     """
     from .search import run_search
     t_wall = time.perf_counter()
@@ -214,9 +221,11 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
                   "device_makespan": res.makespan, "makespan": prop_makespan, "J": J, "chains": chains,
                   "total_wall_s": None, "adopted": True}
 
-    # ---- introspection hysteresis: the documented intent of milp.py:363-442
+    # ---- introspection hysteresis (opt-in): the documented intent of milp.py:363-442
     out = prop + (prop_makespan,)
-    if presolved is not None:
+    if hysteresis is None:
+        hysteresis = os.environ.get("SATURN_B200_HYSTERESIS", "0") not in ("", "0", "false", "False")
+    if presolved is not None and hysteresis:
         p_sta, p_tga, p_bss, p_bna, p_boa, saved = presolved
         same_tasks = p_tga is not None and len(p_tga) == J
         if saved is not None and same_tasks:

@@ -1,0 +1,25 @@
+"""Small run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from saturn_b200.engine import Engine, random_candidates
+from saturn_b200.search import run_search
+from saturn_b200.synth import synth_table
+
+eng = Engine(0)
+for (J, S, G, B) in [(64, 6, 8, 2000), (100, 3, 8, 777), (300, 2, 8, 500)]:
+    T, valid = synth_table(J, S, G, seed=1)
+    eng.set_table(T)
+    opt, prio = random_candidates(eng, B, valid, seed=2)
+    key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=eng.device)
+    a = eng.eval(opt, prio, best_key=key)
+    b = eng.eval(opt, prio, _no_stream=True)
+    c = eng.eval(opt.contiguous(), prio.contiguous())
+    d = eng.eval(opt, prio, _force_generic=True)
+    e, st, mk = eng.eval_full(opt, prio)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d) and torch.equal(a, e)
+    assert eng.validate(opt, prio) == 0
+    r = run_search(eng, chains=2048, rounds=6, use_dist=False)
+    eng.decode(r.opt, r.prio)
+print("sanitize run ok")

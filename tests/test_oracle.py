@@ -127,3 +127,25 @@ def test_ragged_and_edge_tables():
     # ties go to the lowest slot index
     mk, start, mask, _ = R.list_schedule(tab, [om[0][0], om[1][0]], [1, 0], True)
     assert mask[1] == 0b1 and mask[0] == 0b110
+
+
+def test_milp_port_matches_reference_runs(golden):
+    """oracle/ref_milp.py (the MILP restated for scipy/HiGHS, used on the GPU box where the reference
+    tree is absent) reproduces the optimum the UNMODIFIED reference reached on the fast instances."""
+    from oracle import ref_milp
+    done = 0
+    for rec in golden["cases"]:
+        if rec["variant"] != "tight_m" or rec["name"] not in ("K1_J3_g8_seed1", "C1_J4_g12_seed0"):
+            continue
+        tup = [[tuple(x) for x in t] for t in rec["gpu_time_tuples"]]
+        r = ref_milp.solve(tup, time_limit=60)
+        assert r["proven_optimal"] and r["makespan"] == pytest.approx(rec["makespan"], rel=1e-9)
+        assert r["n_vars"] == rec["highs"]["n_vars"]
+        rts = [tup[t][o][1] for t, o in enumerate(r["opt_idx"])]
+        ks = [tup[t][o][0] for t, o in enumerate(r["opt_idx"])]
+        assert R.check_plan(r["start"], r["mask"], rts, ks)[0]
+        done += 1
+    assert done == 2
+    # SURVEY §8a A2/A3 model-size formulas: C1 (measured 89/616), J=5 S=4 (126/1850), C4
+    assert ref_milp.model_size(4, 2) == (89, 616) and ref_milp.model_size(5, 4) == (126, 1850)
+    assert ref_milp.model_size(256, 8) == (71681, 8413696)
