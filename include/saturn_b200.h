@@ -53,6 +53,7 @@ extern "C" {
 #define SB_ABI_VERSION 1
 #define SB_NSLOT 8          /* GPUs per node, reference milp.py:62 */
 #define SB_MAX_STRATEGIES 32 /* 5 strategy bits in an opt byte */
+#define SB_MAX_NODES 8       /* multi-node tables: up to 8 nodes x 8 GPUs */
 
 typedef enum sb_status {
   SB_OK = 0,
@@ -83,8 +84,10 @@ int sb_sync(sb_handle* h);
 
 /* ---- the table (replaces milp.py:77-81 building gpu_time_tuples) --------------------------
  * T: host or device pointer, fp32 [J][S][G]; gcount: host pointer, uint8 [G], values 1..8.
- * nodes must be 1 (multi-node gangs are confined to one node, milp.py:117-137; N > 1 is
- * SB_ERR_UNSUPPORTED in this version).  Builds on the device: the canonical table
+ * nodes: 1..SB_MAX_NODES nodes of 8 GPUs (the reference takes len(ray.nodes()), milp.py:58-62).  A
+ * task runs on exactly one node and its gang takes GPUs of that node only (milp.py:117-137,209-227).
+ * With nodes > 1 candidates are evaluated on the reduced table only (SB_FLAG_REDUCED) and the opt
+ * byte reads (node << 3) | (k - 1).  Builds on the device: the canonical table
  * tab[J][S][8] (column k-1, +inf where no option), and the min-over-strategies table
  * tmin[J][8] with argS[J][8] (first minimum wins, PerformanceEvaluator.py:105-110). */
 int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int S, int G, int nodes);
@@ -122,16 +125,17 @@ int sb_eval_host(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, 
                  unsigned flags, float* makespan_out);
 
 /* ---- full plan of B candidates (slot-exact; used for decode and for parity tests) ---------
- * start_out fp32 [B][J] and slotmask_out u32 [B][J] are indexed by JOB; bit g of the mask =
- * GPU slot g.  Device pointers; start_out / slotmask_out may be NULL. */
+ * start_out fp32 [B][J] and slotmask_out u32 [B][J] are indexed by JOB; bit g (g < 8) of the mask =
+ * GPU slot g of the job's node, bits 16.. = node index.  Device pointers; start_out / slotmask_out
+ * may be NULL. */
 int sb_eval_full(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
                  unsigned flags, float* makespan_out, float* start_out, uint32_t* slotmask_out);
 
 /* decode ONE candidate given in host memory into host arrays (all [J]; any may be NULL):
- * start, slot mask, strategy index s (for SB_FLAG_REDUCED the arg-min strategy of the cell),
- * gpu count k.  makespan (nullable) receives the candidate's makespan. */
+ * start, GPU mask within the node, strategy index s (for SB_FLAG_REDUCED the arg-min strategy of
+ * the cell), gpu count k, node index.  makespan (nullable) receives the candidate's makespan. */
 int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags, float* start,
-              uint32_t* slotmask, uint8_t* strategy, uint8_t* gpus, float* makespan);
+              uint32_t* slotmask, uint8_t* strategy, uint8_t* gpus, uint8_t* node, float* makespan);
 
 /* ---- search (replaces prob.solve(), milp.py:321-327) ---------------------------------------
  * A population of `chains` candidates lives on the device.  sb_search_init seeds it (random

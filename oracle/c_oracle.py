@@ -27,7 +27,7 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                           ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                           ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _lib.ref_eval_max_threads.restype = ctypes.c_int
     return _lib
@@ -37,7 +37,7 @@ def max_threads():
     return int(lib().ref_eval_max_threads())
 
 
-def evaluate(tab, opt, prio, integer_starts=True, dtype=np.float32, nslot=8, want_plan=False, threads=0):
+def evaluate(tab, opt, prio, integer_starts=True, dtype=np.float32, nslot=8, want_plan=False, threads=0, nodes=1):
     """tab[J][S][8], opt[B][J] u8, prio[B][J] u8/u16 -> makespan[B] (+ start, mask)."""
     tab = np.ascontiguousarray(tab, dtype=dtype)
     J, S, W = tab.shape
@@ -52,7 +52,7 @@ def evaluate(tab, opt, prio, integer_starts=True, dtype=np.float32, nslot=8, wan
     mask = np.zeros((B, J), dtype=np.uint32) if want_plan else None
     fn = lib().ref_eval_f32 if dtype == np.float32 else lib().ref_eval_f64
     rc = fn(tab.ctypes.data, J, S, opt.ctypes.data, prio.ctypes.data, prio.dtype.itemsize, B,
-            int(bool(integer_starts)), nslot, mk.ctypes.data,
+            int(bool(integer_starts)), nslot, int(nodes), mk.ctypes.data,
             start.ctypes.data if want_plan else None, mask.ctypes.data if want_plan else None,
             int(threads))
     if rc != 0:

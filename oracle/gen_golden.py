@@ -118,7 +118,44 @@ def run_case(mod, Strategy, pulp, name, tuples, timeout):
     return rec
 
 
+def main_nodes(nodes):
+    """Multi-node fixtures: the reference with ray.nodes() reporting `nodes` nodes (milp.py:58)."""
+    os.environ["ORACLE_RAY_NODES"] = str(nodes)
+    milp, tight, Strategy, pulp = _load_reference()
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import ref_eval as R
+    cases = [
+        ("N2_K1_J3_g8_seed1", probe_tuples(3, [8], 1), 120),
+        ("N2_J4_g48_seed5", probe_tuples(4, [4, 8], 5), 240),
+        ("N2_J3_g1248_seed0", probe_tuples(3, [1, 2, 4, 8], 0), 240),
+        ("N2_J5_g8_seed4", probe_tuples(5, [8], 4), 240),
+    ]
+    out = {"generator": "oracle/gen_golden.py --nodes %d" % nodes, "reference_commit": "b65e3d2", "nodes": nodes,
+           "scipy": __import__("scipy").__version__, "cases": []}
+    for name, tuples, timeout in cases:
+        rec = run_case(tight, Strategy, pulp, name, tuples, timeout)
+        rec["variant"] = "tight_m"
+        rec["proven_optimal"] = bool(rec["highs"].get("status") == 0)
+        if rec["incumbent"]:
+            plan = R.plan_from_arrays(tuples, rec["sta"], rec["tga"], rec["bss"], rec["bna"])
+            ok, ov, mk = R.check_plan([p[0] for p in plan], [p[1] << (8 * p[5]) for p in plan],
+                                      [p[2] for p in plan], [p[3] for p in plan], nslot=8 * nodes)
+            rec["overlaps"], rec["feasible"] = ov, bool(ok)
+        tab, optmap = R.table_from_tuples(tuples)
+        bf = R.brute_force(tab, optmap, integer_starts=True, nodes=nodes)
+        rec["bruteforce_int"] = {"makespan": bf[0], "opt": list(bf[1]), "prio": list(bf[2])}
+        print(name, "status", rec["highs"].get("status"), "mk", rec.get("makespan"), "bf", bf[0],
+              "overlaps", rec.get("overlaps"), "%.1fs" % rec["solver_wall_s"], flush=True)
+        out["cases"].append(rec)
+    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "milp_cases_n%d.json" % nodes)
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", dst)
+
+
 def main():
+    if "--nodes" in sys.argv:
+        return main_nodes(int(sys.argv[sys.argv.index("--nodes") + 1]))
     milp, tight, Strategy, pulp = _load_reference()
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import ref_eval as R

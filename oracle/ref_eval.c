@@ -27,25 +27,27 @@
 #endif
 
 #define NSLOT_MAX 8
+#define NODES_MAX 8   /* multi-node: opt byte = (node << 3) | (k - 1), reduced table (S = 1) */
 
 #define DEFINE_EVAL(NAME, REAL, CEIL)                                                         \
   int NAME(const REAL* tab, int J, int S, const uint8_t* opt, const void* prio,              \
-           int prio_bytes, int64_t B, int integer_starts, int nslot, REAL* makespan,         \
+           int prio_bytes, int64_t B, int integer_starts, int nslot, int nodes, REAL* makespan, \
            REAL* start_out, uint32_t* mask_out, int nthreads) {                              \
     if (J <= 0 || S <= 0 || nslot < 1 || nslot > NSLOT_MAX) return -1;                       \
+    if (nodes < 1 || nodes > NODES_MAX || (nodes > 1 && S != 1)) return -3;                  \
     if (prio_bytes != 1 && prio_bytes != 2) return -2;                                       \
     if (nthreads > 0) {                                                                      \
       _Pragma("omp parallel for schedule(static) num_threads(nthreads)")                     \
       for (int64_t b = 0; b < B; ++b) {                                                      \
         NAME##_one(tab, J, S, opt + (size_t)b * J, (const uint8_t*)prio +                    \
-                   (size_t)b * J * prio_bytes, prio_bytes, integer_starts, nslot,            \
+                   (size_t)b * J * prio_bytes, prio_bytes, integer_starts, nslot, nodes,     \
                    makespan + b, start_out ? start_out + (size_t)b * J : 0,                  \
                    mask_out ? mask_out + (size_t)b * J : 0);                                 \
       }                                                                                      \
     } else {                                                                                 \
       for (int64_t b = 0; b < B; ++b)                                                        \
         NAME##_one(tab, J, S, opt + (size_t)b * J, (const uint8_t*)prio +                    \
-                   (size_t)b * J * prio_bytes, prio_bytes, integer_starts, nslot,            \
+                   (size_t)b * J * prio_bytes, prio_bytes, integer_starts, nslot, nodes,     \
                    makespan + b, start_out ? start_out + (size_t)b * J : 0,                  \
                    mask_out ? mask_out + (size_t)b * J : 0);                                 \
     }                                                                                        \
@@ -55,19 +57,22 @@
 #define DEFINE_ONE(NAME, REAL, CEIL)                                                          \
   static void NAME##_one(const REAL* tab, int J, int S, const uint8_t* opt,                  \
                          const uint8_t* prio, int prio_bytes, int integer_starts,            \
-                         int nslot, REAL* makespan, REAL* start_out, uint32_t* mask_out) {   \
-    REAL ready[NSLOT_MAX];                                                                   \
+                         int nslot, int nodes, REAL* makespan, REAL* start_out,              \
+                         uint32_t* mask_out) {                                               \
+    REAL ready_all[NODES_MAX * NSLOT_MAX];                                                   \
     int order[NSLOT_MAX];                                                                    \
     REAL mk = 0;                                                                             \
     int bad = 0;                                                                             \
     (void)S;                                                                                 \
-    for (int g = 0; g < nslot; ++g) ready[g] = 0;                                            \
+    for (int g = 0; g < NODES_MAX * NSLOT_MAX; ++g) ready_all[g] = 0;                        \
     for (int i = 0; i < J; ++i) {                                                            \
       int j = prio_bytes == 1 ? prio[i] : ((const uint16_t*)prio)[i];                        \
       int o = opt[j];                                                                        \
       int k = (o & 7) + 1;                                                                   \
-      REAL rt = tab[(size_t)j * S * 8 + o];                                                  \
-      if (k > nslot) { bad = 1; break; }                                                     \
+      int node = nodes > 1 ? (o >> 3) : 0;                                                   \
+      REAL rt = tab[(size_t)j * S * 8 + (nodes > 1 ? (o & 7) : o)];                          \
+      if (k > nslot || node >= nodes) { bad = 1; break; }                                    \
+      REAL* ready = ready_all + node * NSLOT_MAX;                                            \
       /* order slots by (ready, slot): insertion sort, stable => ties keep slot order */     \
       for (int g = 0; g < nslot; ++g) {                                                      \
         int p = g;                                                                           \
@@ -80,7 +85,7 @@
       uint32_t m = 0;                                                                        \
       for (int q = 0; q < k; ++q) { ready[order[q]] = nxt; m |= 1u << order[q]; }            \
       if (start_out) start_out[j] = s;                                                       \
-      if (mask_out) mask_out[j] = m;                                                         \
+      if (mask_out) mask_out[j] = ((uint32_t)node << 16) | m;                                \
       REAL c = s + rt;                                                                       \
       if (c > mk) mk = c;                                                                    \
     }                                                                                        \

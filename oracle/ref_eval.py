@@ -118,14 +118,21 @@ def table_from_tuples(gpu_time_tuples) -> Tuple[np.ndarray, List[List[int]]]:
 
 
 # --------------------------------------------------------------------------- evaluator
-def list_schedule(tab, opt, prio, integer_starts=True, dtype=np.float64, nslot=NSLOT):
-    """One candidate, pure Python loops.  Returns (makespan, start[J], mask[J], ready[nslot]).
+def list_schedule(tab, opt, prio, integer_starts=True, dtype=np.float64, nslot=NSLOT, nodes=1):
+    """One candidate, pure Python loops.  Returns (makespan, start[J], mask[J], ready).
 
     `dtype` selects the arithmetic (np.float64 = exact restatement,
     np.float32 = the arithmetic of the CUDA path, bit-for-bit).
+
+    nodes > 1 (multi-node, reference milp.py:117-137,209-227: a task runs on exactly ONE node and
+    its gang takes GPUs of that node only): the table must be the reduced one (S = 1) and the opt
+    byte reads (node << 3) | (k - 1); mask[j] = (node << 16) | gpu bitmask within the node; a node
+    index >= nodes makes the candidate infeasible (inf).
     """
     f = dtype
     J = len(prio)
+    if nodes > 1:
+        return _list_schedule_nodes(tab, opt, prio, integer_starts, f, nslot, nodes)
     ready = [f(0.0)] * nslot
     start = [f(0.0)] * J
     mask = [0] * J
@@ -148,6 +155,38 @@ def list_schedule(tab, opt, prio, integer_starts=True, dtype=np.float64, nslot=N
             m |= 1 << g
         start[j] = s
         mask[j] = m
+        c = f(s + rt)
+        if c > mk:
+            mk = c
+    return float(mk), start, mask, ready
+
+
+def _list_schedule_nodes(tab, opt, prio, integer_starts, f, nslot, nodes):
+    J = len(prio)
+    ready = [[f(0.0)] * nslot for _ in range(nodes)]
+    start = [f(0.0)] * J
+    mask = [0] * J
+    mk = f(0.0)
+    for i in range(J):
+        j = int(prio[i])
+        o = int(opt[j])
+        k = (o & 7) + 1
+        n = o >> 3
+        rt = f(tab[j][0][o & 7])
+        if k > nslot or n >= nodes:
+            return float("inf"), start, mask, ready
+        rd = ready[n]
+        order = sorted(range(nslot), key=lambda g: (rd[g], g))
+        sel = order[:k]
+        s = rd[sel[-1]]
+        hold = f(math.ceil(rt)) if (integer_starts and math.isfinite(rt)) else rt
+        nxt = f(s + hold)
+        m = 0
+        for g in sel:
+            rd[g] = nxt
+            m |= 1 << g
+        start[j] = s
+        mask[j] = (n << 16) | m
         c = f(s + rt)
         if c > mk:
             mk = c
@@ -202,13 +241,16 @@ def list_schedule_batch(tab, opt, prio, integer_starts=True, dtype=np.float64, n
 
 
 def brute_force(tab, valid_opts: Sequence[Sequence[int]], integer_starts=True, nslot=NSLOT,
-                dtype=np.float64):
-    """Exhaustive minimum over all (option vector, permutation) candidates (J <= ~6)."""
+                dtype=np.float64, nodes=1):
+    """Exhaustive minimum over all (option vector, permutation) candidates (J <= ~6).
+    With nodes > 1 every option byte (k - 1) is combined with every node index."""
     J = len(valid_opts)
     best = (INF, None, None)
+    if nodes > 1:
+        valid_opts = [[(n << 3) | (o & 7) for o in ops for n in range(nodes)] for ops in valid_opts]
     for ov in itertools.product(*valid_opts):
         for perm in itertools.permutations(range(J)):
-            mk, _, _, _ = list_schedule(tab, ov, perm, integer_starts, dtype, nslot)
+            mk, _, _, _ = list_schedule(tab, ov, perm, integer_starts, dtype, nslot, nodes)
             if mk < best[0]:
                 best = (mk, tuple(ov), tuple(perm))
     return best

@@ -1,7 +1,7 @@
 """Minimal stand-in for the slice of Ray the reference's import chain touches.
 
-ORACLE INFRASTRUCTURE ONLY (see oracle/shims/pulp.py).  One node, 8 GPUs —
-which is what the reference solver assumes anyway (milp.py:57-62, DEBUG = True).
+ORACLE INFRASTRUCTURE ONLY (see oracle/shims/pulp.py).  ORACLE_RAY_NODES nodes (default one) of
+8 GPUs each — 8 per node is what the reference solver assumes anyway (milp.py:57-62, DEBUG = True).
 """
 
 
@@ -14,7 +14,9 @@ def init(*a, **k):
 
 
 def nodes():
-    return [{"Resources": {"GPU": 8, "CPU": 8}}]
+    import os
+    n = int(os.environ.get("ORACLE_RAY_NODES", "1"))    # multi-node fixtures: N nodes x 8 GPUs
+    return [{"Resources": {"GPU": 8, "CPU": 8}} for _ in range(n)]
 
 
 def get(x):

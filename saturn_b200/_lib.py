@@ -57,7 +57,7 @@ def load():
         "sb_validate": [vp, vp, vp, i64, i64, u32, C.POINTER(i64)],
         "sb_eval_host": [vp, vp, vp, i64, i64, u32, vp],
         "sb_eval_full": [vp, vp, vp, i64, i64, u32, vp, vp, vp],
-        "sb_decode": [vp, vp, vp, u32, vp, vp, vp, vp, vp],
+        "sb_decode": [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp],
         "sb_search_init": [vp, C.POINTER(SearchParams), vp, vp],
         "sb_search_round": [vp, ci],
         "sb_search_best_key_ptr": [vp, C.POINTER(vp)],

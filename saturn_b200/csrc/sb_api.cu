@@ -49,6 +49,7 @@ struct sb_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int J = 0, S = 0;
+  int nodes = 1;
   float sentinel = kSentinel;
   float* tab = nullptr;
   float* tmin = nullptr;
@@ -167,7 +168,7 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   if (J < 1 || J > 65535) return fail(SB_ERR_ARG, "J=%d outside 1..65535", J);
   if (S < 1 || S > SB_MAX_STRATEGIES) return fail(SB_ERR_ARG, "S=%d outside 1..%d", S, SB_MAX_STRATEGIES);
   if (G < 1 || G > SB_NSLOT) return fail(SB_ERR_ARG, "G=%d outside 1..%d", G, SB_NSLOT);
-  if (nodes != 1) return fail(SB_ERR_UNSUPPORTED, "nodes=%d: only single-node tables are supported", nodes);
+  if (nodes < 1 || nodes > SB_MAX_NODES) return fail(SB_ERR_ARG, "nodes=%d outside 1..%d", nodes, SB_MAX_NODES);
   uint64_t packed = 0;
   for (int g = 0; g < G; ++g) {
     if (gcount[g] < 1 || gcount[g] > SB_NSLOT) return fail(SB_ERR_ARG, "gcount[%d]=%d outside 1..8", g, gcount[g]);
@@ -213,6 +214,7 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   }
   h->J = J;
   h->S = S;
+  h->nodes = nodes;
   return SB_OK;
 }
 
@@ -240,6 +242,10 @@ static int make_call(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
   if (B > 0xffffffffll) return fail(SB_ERR_ARG, "B=%lld exceeds 2^32-1 candidates per call", static_cast<long long>(B));
   const int pb = h->J <= 256 ? 1 : 2;
   const bool reduced = (flags & SB_FLAG_REDUCED) != 0;
+  if (h->nodes > 1 && !reduced)
+    return fail(SB_ERR_UNSUPPORTED, "a %d-node table is evaluated on the reduced table only: pass SB_FLAG_REDUCED "
+                "(opt byte = (node << 3) | (k - 1))", h->nodes);
+  c->nodes = h->nodes;
   c->tab = reduced ? h->tmin : h->tab;
   c->J = h->J;
   c->SG = (reduced ? 1 : h->S) * kSlots;
@@ -351,7 +357,7 @@ int sb_eval_host(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, 
 }
 
 int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags, float* start, uint32_t* slotmask,
-              uint8_t* strategy, uint8_t* gpus, float* makespan) {
+              uint8_t* strategy, uint8_t* gpus, uint8_t* node, float* makespan) {
   int rc = use_device(h);
   if (rc) return rc;
   if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
@@ -389,10 +395,12 @@ int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags
   const bool reduced = (flags & SB_FLAG_REDUCED) != 0;
   for (int j = 0; j < J; ++j) {
     if (start) start[j] = hs[j];
-    if (slotmask) slotmask[j] = hm[j];
+    if (slotmask) slotmask[j] = hm[j] & 0xffffu;
+    if (node) node[j] = static_cast<uint8_t>(hm[j] >> 16);
     const int col = opt[j] & 7;
     if (gpus) gpus[j] = static_cast<uint8_t>(col + 1);
-    if (strategy) strategy[j] = reduced ? h->h_args[static_cast<size_t>(j) * kSlots + col] : static_cast<uint8_t>(opt[j] >> 3);
+    if (strategy)
+      strategy[j] = reduced ? h->h_args[static_cast<size_t>(j) * kSlots + col] : static_cast<uint8_t>(opt[j] >> 3);
   }
   if (makespan) *makespan = mk;
   return SB_OK;
@@ -437,6 +445,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   SearchDev& d = s.d;
   d.J = J;
   d.pb = pb;
+  d.nodes = h->nodes;
   d.chains = p->chains;
   d.chain_base = p->chain_base;
   d.seed = p->seed;
@@ -444,6 +453,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   // make stride_p == stride_o * pb so that one element stride describes both (sb_eval contract)
   d.stride_p = d.stride_o * pb;
   const bool reduced = (p->flags & SB_FLAG_REDUCED) != 0;
+  if (h->nodes > 1 && !reduced) return fail(SB_ERR_UNSUPPORTED, "multi-node search needs SB_FLAG_REDUCED");
   d.vopt = h->vopt[reduced ? 1 : 0];
   d.nvalid = h->nvalid[reduced ? 1 : 0];
   const size_t P = static_cast<size_t>(d.chains);

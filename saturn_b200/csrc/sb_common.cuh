@@ -13,6 +13,7 @@ namespace sb {
 
 constexpr int kSlots = SB_NSLOT;
 constexpr int kWarp = 32;
+constexpr int kMaxNodes = SB_MAX_NODES;
 constexpr float kSentinel = 1.0e6f;  // reference's "unprofiled" runtime, PerformanceEvaluator.py:99
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
@@ -106,7 +107,9 @@ __device__ __forceinline__ float copy_fadd(float x, float negzero) {
   return r;
 }
 
-template <bool kIntegerStarts>
+// kTrackMk: fold this job's completion (s + rt) into mk.  Needed with integer starts (the slot
+// state holds s + ceil(rt), not the completion) and with several nodes (no single f[7] at the end).
+template <bool kIntegerStarts, bool kTrackMk = kIntegerStarts>
 __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1, int one) {
   const float INF = inf_f();
   const int b1 = km1 & 2, b0 = km1 & 1;
@@ -144,9 +147,10 @@ __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int 
   if (kIntegerStarts) {
     // every entry of f is an integer here, so s is; the slot is usable again at s + ceil(rt)
     v = s + ceilf(rt);
-    mk = fmaxf(mk, s + rt);
+    if (kTrackMk) mk = fmaxf(mk, s + rt);
   } else {
     v = s + rt;
+    if (kTrackMk) mk = fmaxf(mk, v);
   }
   f[0] = fmaxf(f[0], fminf(v, x1));
   f[1] = fmaxf(f[1], fminf(v, x2));

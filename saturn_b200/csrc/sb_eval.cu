@@ -3,7 +3,7 @@
 // Replaces the arithmetic the reference hands to Gurobi/CBC (saturn/solver/milp.py:321-327):
 // instead of branch-and-bound over the MILP of milp.py:96-319, B candidates
 // (option vector, priority permutation) are scored in parallel; each score is the makespan the
-// MILP's constraints would force for that choice of strategies / GPU counts / ordering.
+// MILP's constraints would force for that choice of strategies / GPU counts / nodes / ordering.
 //
 // Kernel shape (k_eval_tiles):
 //   * persistent grid, one CTA per SM, NW warps per CTA; the J x S x 8 runtime table is staged
@@ -18,8 +18,11 @@
 //     scheduler 31 % of issue slots were lost to dependency waits).  Unaligned rows fall back to
 //     the non-STREAM variant (prio rows staged in shared memory, TMA or plain loads);
 //   * one candidate per LANE: the 8 slot ready-times live sorted in 8 registers and one
-//     scheduling step is ~45 predicated selects / min / max (sb_common.cuh: ls_step) — fp32
-//     min/max/add and byte indexing only, no tensor cores;
+//     scheduling step is ~57 instructions (sb_common.cuh: ls_step) — fp32 min/max/add and byte
+//     indexing only, no tensor cores;
+//   * MULTI variant (several nodes, milp.py:117-137: a gang stays inside one node): the sorted
+//     state of every node lives in a lane-private shared-memory column (2 x float4 per node,
+//     conflict-free); a step loads the state of the job's node, updates it, stores it back;
 //   * makespans are written coalesced (128 B per warp); an optional 64-bit arg-min key is
 //     folded with one redux + one atomicMin per warp.
 #include "sb_internal.h"
@@ -36,18 +39,13 @@ struct TileArgs {
   int row_o, row_p;              // shared-memory row strides (bytes, odd multiple of 16)
   int copy_o, copy_p;            // bytes per row copy (multiple of 16)
   int use_bulk;                  // rows are 16-byte aligned -> TMA bulk copies
+  int nodes;                     // MULTI: number of nodes (2..kMaxNodes)
   float* out;
   unsigned long long* best_key;
   uint32_t id_base;
   long long ntiles;
   int one;  // run-time 1 (see pmov_fma)
 };
-
-template <int PB>
-__device__ __forceinline__ int prio_at(const uint32_t (&w)[4], int t) {
-  if (PB == 1) return (w[t >> 2] >> ((t & 3) * 8)) & 0xff;
-  return (w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
-}
 
 struct PrioChunk {
   uint32_t w[8];  // 32 bytes = 32 (u8) or 16 (u16) schedule positions
@@ -61,7 +59,63 @@ __device__ __forceinline__ PrioChunk ld_prio32(const uint8_t* p) {
   return c;
 }
 
-template <int PB, bool INT, bool STREAM>
+// Per-lane evaluation state + the per-job step.
+template <bool INT, bool MULTI>
+struct LaneState {
+  float f[8];
+  float mk;
+  const uint8_t* orow;  // this candidate's opt bytes (shared memory or global)
+  const float* tab;     // runtime table (shared memory or global)
+  int SG;
+  int one;
+  float4* ns;  // MULTI: lane-private node-state column; node n lives at ns[(2n)*32], ns[(2n+1)*32]
+
+  __device__ __forceinline__ void reset(int nodes) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    mk = 0.f;
+    if (MULTI) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int n = 0; n < 2 * nodes; ++n) ns[n * 32] = z;
+    }
+  }
+  __device__ __forceinline__ void step(int j) {
+    const int o = orow[j];
+    if (!MULTI) {
+      const float rt = tab[j * SG + o];
+      ls_step<INT>(f, mk, rt, o & 7, one);
+    } else {
+      const int col = o & 7, n = o >> 3;  // reduced table only: opt = (node << 3) | (k - 1)
+      const float rt = tab[j * 8 + col];
+      float4* slot = ns + (2 * n) * 32;
+      const float4 lo = slot[0], hi = slot[32];
+      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
+      f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+      ls_step<INT, true>(f, mk, rt, col, one);
+      slot[0] = make_float4(f[0], f[1], f[2], f[3]);
+      slot[32] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+  __device__ __forceinline__ float result() const { return (INT || MULTI) ? mk : f[7]; }
+};
+
+template <int PB>
+__device__ __forceinline__ int prio_at(const uint32_t* w, int t) {
+  if (PB == 1) return (w[t >> 2] >> ((t & 3) * 8)) & 0xff;
+  return (w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
+}
+
+__device__ __forceinline__ void fold_best(unsigned long long* best_key, bool active, float mk, uint32_t id, int lane) {
+  const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
+  const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+  const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
+  if (lane == __ffs(who) - 1 && active) {
+    const unsigned long long key = pack_key(mk, id);
+    if (key < *reinterpret_cast<volatile unsigned long long*>(best_key)) atomicMin(best_key, key);
+  }
+}
+
+template <int PB, bool INT, bool STREAM, bool MULTI>
 __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const TileArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
@@ -70,8 +124,11 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
   float* tab_s = reinterpret_cast<float*>(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((tab_bytes + 15u) & ~15u));
   uint8_t* tiles = reinterpret_cast<uint8_t*>(bars) + (((1 + nw) * 8 + 15) & ~15);
-  const uint32_t tile_bytes = 32u * (a.row_o + (STREAM ? 0 : a.row_p));
-  uint8_t* tile_o = tiles + static_cast<size_t>(warp) * tile_bytes;
+  const uint32_t node_bytes = MULTI ? static_cast<uint32_t>(a.nodes) * 1024u : 0u;
+  const uint32_t tile_bytes = 32u * (a.row_o + (STREAM ? 0 : a.row_p)) + node_bytes;
+  uint8_t* wbase = tiles + static_cast<size_t>(warp) * tile_bytes;
+  float4* node_s = reinterpret_cast<float4*>(wbase);  // [2*nodes][32] float4, first (16-byte aligned)
+  uint8_t* tile_o = wbase + node_bytes;
   uint8_t* tile_p = tile_o + 32u * a.row_o;
   uint64_t* bar_tab = bars;
   uint64_t* bar_w = bars + 1 + warp;
@@ -92,6 +149,13 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
     }
   }
 
+  LaneState<INT, MULTI> st;
+  st.tab = tab_s;
+  st.SG = a.SG;
+  st.one = a.one;
+  st.orow = tile_o + lane * a.row_o;
+  st.ns = node_s + lane;
+
   uint32_t phase = 0;
   bool tab_ready = false;
   for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
@@ -99,8 +163,10 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
     const long long b0 = tile * 32;
     const int nb = static_cast<int>(min(32ll, a.B - b0));
     const bool active = lane < nb;
+    const uint8_t* pg = a.prio + (b0 + lane) * a.stride_p;
     // ---- fetch this warp's 32 candidate rows
     __syncwarp();
+    PrioChunk q;
     if (a.use_bulk) {
       fence_proxy_async();  // order the previous tile's generic-proxy reads before async writes
       if (lane == 0)
@@ -108,66 +174,11 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
       __syncwarp();
       if (active) {
         tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + (b0 + lane) * a.stride_o, a.copy_o, bar_w);
-        if (!STREAM) tma_bulk_g2s(tile_p + lane * a.row_p, a.prio + (b0 + lane) * a.stride_p, a.copy_p, bar_w);
+        if (!STREAM) tma_bulk_g2s(tile_p + lane * a.row_p, pg, a.copy_p, bar_w);
       }
-      PrioChunk q;
-      if (STREAM && active) q = ld_prio32(a.prio + (b0 + lane) * a.stride_p);  // overlaps the TMA wait
+      if (STREAM && active) q = ld_prio32(pg);  // overlaps the TMA wait
       mbar_wait(bar_w, phase);
       phase ^= 1;
-      if (STREAM) {
-        if (!tab_ready) {
-          mbar_wait(bar_tab, 0);
-          tab_ready = true;
-        }
-        float mk = 0.f;
-        if (active) {
-          const uint8_t* orow = tile_o + lane * a.row_o;
-          const uint8_t* pg = a.prio + (b0 + lane) * a.stride_p;
-          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          constexpr int STEPS = 32 / PB;  // schedule positions per 256-bit load
-          const int one = a.one;
-          const int SG = a.SG;
-          const int J = a.J;
-          const int nch = (J + STEPS - 1) / STEPS;
-          for (int c = 0; c < nch; ++c) {
-            PrioChunk nxt = q;
-            if (c + 1 < nch) nxt = ld_prio32(pg + (c + 1) * 32);
-            if ((c + 1) * STEPS <= J) {
-#pragma unroll
-              for (int t = 0; t < STEPS; ++t) {
-                const int j = PB == 1 ? (q.w[t >> 2] >> ((t & 3) * 8)) & 0xff : (q.w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
-                const int o = orow[j];
-                const float rt = tab_s[j * SG + o];
-                ls_step<INT>(f, mk, rt, o & 7, one);
-              }
-            } else {
-              const int rem = J - c * STEPS;
-#pragma unroll
-              for (int t = 0; t < STEPS; ++t) {
-                if (t < rem) {
-                  const int j = PB == 1 ? (q.w[t >> 2] >> ((t & 3) * 8)) & 0xff : (q.w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
-                  const int o = orow[j];
-                  const float rt = tab_s[j * SG + o];
-                  ls_step<INT>(f, mk, rt, o & 7, one);
-                }
-              }
-            }
-            q = nxt;
-          }
-          if (!INT) mk = f[7];
-          a.out[b0 + lane] = mk;
-        }
-        if (a.best_key != nullptr) {
-          const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
-          const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-          const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
-          if (lane == __ffs(who) - 1 && active) {
-            const unsigned long long key = pack_key(mk, a.id_base + static_cast<uint32_t>(b0 + lane));
-            if (key < *reinterpret_cast<volatile unsigned long long*>(a.best_key)) atomicMin(a.best_key, key);
-          }
-        }
-        continue;
-      }
     } else {
       for (int r = 0; r < nb; ++r) {
         const uint8_t* so = a.opt + (b0 + r) * a.stride_o;
@@ -184,50 +195,47 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
     // ---- one candidate per lane
     float mk = 0.f;
     if (active) {
-      const uint8_t* orow = tile_o + lane * a.row_o;
-      const uint4* prow = reinterpret_cast<const uint4*>(tile_p + lane * a.row_p);
-      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      constexpr int STEPS = 16 / PB;  // jobs per 128-bit prio read
-      const int one = a.one;
-      const int nfull = a.J / STEPS;
-      const int SG = a.SG;
-      for (int c = 0; c < nfull; ++c) {
-        const uint4 p = prow[c];
-        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+      st.reset(a.nodes);
+      const int J = a.J;
+      if (STREAM) {
+        constexpr int STEPS = 32 / PB;  // schedule positions per 256-bit load
+        const int nch = (J + STEPS - 1) / STEPS;
+        for (int c = 0; c < nch; ++c) {
+          PrioChunk nxt = q;
+          if (c + 1 < nch) nxt = ld_prio32(pg + (c + 1) * 32);
+          if ((c + 1) * STEPS <= J) {
 #pragma unroll
-        for (int t = 0; t < STEPS; ++t) {
-          const int j = prio_at<PB>(w, t);
-          const int o = orow[j];
-          const float rt = tab_s[j * SG + o];
-          ls_step<INT>(f, mk, rt, o & 7, one);
+            for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(q.w, t));
+          } else {
+            const int rem = J - c * STEPS;
+#pragma unroll
+            for (int t = 0; t < STEPS; ++t)
+              if (t < rem) st.step(prio_at<PB>(q.w, t));
+          }
+          q = nxt;
         }
-      }
-      const int rem = a.J - nfull * STEPS;
-      if (rem > 0) {
-        const uint4 p = prow[nfull];
-        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+      } else {
+        const uint4* prow = reinterpret_cast<const uint4*>(tile_p + lane * a.row_p);
+        constexpr int STEPS = 16 / PB;  // jobs per 128-bit shared-memory read
+        const int nch = (J + STEPS - 1) / STEPS;
+        for (int c = 0; c < nch; ++c) {
+          const uint4 p = prow[c];
+          const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+          if ((c + 1) * STEPS <= J) {
 #pragma unroll
-        for (int t = 0; t < STEPS; ++t) {
-          if (t < rem) {
-            const int j = prio_at<PB>(w, t);
-            const int o = orow[j];
-            const float rt = tab_s[j * SG + o];
-            ls_step<INT>(f, mk, rt, o & 7, one);
+            for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(w, t));
+          } else {
+            const int rem = J - c * STEPS;
+#pragma unroll
+            for (int t = 0; t < STEPS; ++t)
+              if (t < rem) st.step(prio_at<PB>(w, t));
           }
         }
       }
-      if (!INT) mk = f[7];
+      mk = st.result();
       a.out[b0 + lane] = mk;
     }
-    if (a.best_key != nullptr) {
-      const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
-      const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-      const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
-      if (lane == __ffs(who) - 1 && active) {
-        const unsigned long long key = pack_key(mk, a.id_base + static_cast<uint32_t>(b0 + lane));
-        if (key < *reinterpret_cast<volatile unsigned long long*>(a.best_key)) atomicMin(a.best_key, key);
-      }
-    }
+    if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b0 + lane), lane);
   }
   if (!tab_ready && threadIdx.x == 0) mbar_wait(bar_tab, 0);  // never leave a bulk copy in flight
 }
@@ -235,6 +243,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
 // ------------------------------------------------------------------------------------------
 // Generic fallback: any J (prio u8/u16), any row stride; rows are read straight from global
 // memory through L1.  The table is staged in shared memory when it fits, else read via L1/L2.
+// MULTI keeps the node states in a lane-private shared-memory column as the tile kernel does.
 struct GenericArgs {
   const float* tab;
   int J, SG;
@@ -246,49 +255,43 @@ struct GenericArgs {
   unsigned long long* best_key;
   uint32_t id_base;
   int tab_in_smem;
+  int nodes;
   int one;
 };
 
-template <int PB, bool INT>
+template <int PB, bool INT, bool MULTI>
 __global__ void __launch_bounds__(128) k_eval_generic(const GenericArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const float* tab = a.tab;
+  const uint32_t node_bytes = MULTI ? static_cast<uint32_t>(a.nodes) * 1024u : 0u;  // per warp
+  float4* node_s = reinterpret_cast<float4*>(smem) + (threadIdx.x >> 5) * (node_bytes / 16);
   if (a.tab_in_smem) {
-    float* tab_s = reinterpret_cast<float*>(smem);
+    float* tab_s = reinterpret_cast<float*>(smem + (blockDim.x >> 5) * node_bytes);
     const int n = a.J * a.SG;
     for (int i = threadIdx.x; i < n; i += blockDim.x) tab_s[i] = a.tab[i];
     __syncthreads();
     tab = tab_s;
   }
   const int lane = threadIdx.x & 31;
+  LaneState<INT, MULTI> st;
+  st.tab = tab;
+  st.SG = a.SG;
+  st.one = a.one;
+  st.ns = node_s + lane;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long Bpad = (a.B + 31) & ~31ll;
   for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < Bpad; b += nthreads) {
     const bool active = b < a.B;
     float mk = 0.f;
     if (active) {
-      const uint8_t* orow = a.opt + b * a.stride_o;
+      st.orow = a.opt + b * a.stride_o;
       const uint8_t* prow = a.prio + b * a.stride_p;
-      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const int one = a.one;
-      for (int i = 0; i < a.J; ++i) {
-        const int j = PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i];
-        const int o = orow[j];
-        const float rt = tab[j * a.SG + o];
-        ls_step<INT>(f, mk, rt, o & 7, one);
-      }
-      if (!INT) mk = f[7];
+      st.reset(a.nodes);
+      for (int i = 0; i < a.J; ++i) st.step(PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i]);
+      mk = st.result();
       a.out[b] = mk;
     }
-    if (a.best_key != nullptr) {
-      const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
-      const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-      const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
-      if (lane == __ffs(who) - 1 && active) {
-        const unsigned long long key = pack_key(mk, a.id_base + static_cast<uint32_t>(b));
-        if (key < *reinterpret_cast<volatile unsigned long long*>(a.best_key)) atomicMin(a.best_key, key);
-      }
-    }
+    if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b), lane);
   }
 }
 
@@ -296,7 +299,8 @@ __global__ void __launch_bounds__(128) k_eval_generic(const GenericArgs a) {
 // Slot-exact evaluation: start time and GPU-slot bitmask per job.  The k slots with smallest
 // (ready, slot) are found by k ascending scans with a strict '<' (lowest slot wins ties),
 // exactly as the oracle states the rule.  Not a throughput kernel: used to decode winners and
-// for the slot-index parity tests.
+// for the slot-index parity tests.  With nodes > 1 the opt byte is (node << 3) | (k - 1), the
+// scans run over the job's node only, and the mask is (node << 16) | gpu bits.
 struct FullArgs {
   const float* tab;
   int J, SG;
@@ -304,6 +308,7 @@ struct FullArgs {
   const uint8_t* prio;
   long long B;
   long long stride_o, stride_p;
+  int nodes;
   float* out;
   float* start;         // [B][J] by job, nullable
   uint32_t* slotmask;   // [B][J] by job, nullable
@@ -312,29 +317,30 @@ struct FullArgs {
 template <int PB, bool INT>
 __global__ void __launch_bounds__(128) k_eval_full(const FullArgs a) {
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool multi = a.nodes > 1;
   for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < a.B; b += nthreads) {
     const uint8_t* orow = a.opt + b * a.stride_o;
     const uint8_t* prow = a.prio + b * a.stride_p;
-    float ready[kSlots];
-#pragma unroll
-    for (int g = 0; g < kSlots; ++g) ready[g] = 0.f;
+    float ready[kMaxNodes * kSlots];
+    for (int g = 0; g < a.nodes * kSlots; ++g) ready[g] = 0.f;
     float mk = 0.f;
     for (int i = 0; i < a.J; ++i) {
       const int j = PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i];
       const int o = orow[j];
       const int k = (o & 7) + 1;
-      const float rt = __ldg(a.tab + static_cast<size_t>(j) * a.SG + o);
+      const int node = multi ? (o >> 3) : 0;
+      const float rt = __ldg(a.tab + static_cast<size_t>(j) * a.SG + (multi ? (o & 7) : o));
+      float* rd = ready + node * kSlots;
       uint32_t taken = 0;
       float s = 0.f;
       for (int q = 0; q < k; ++q) {
         int best = -1;
         float bv = 0.f;
-#pragma unroll
         for (int g = 0; g < kSlots; ++g) {
           const bool free_slot = ((taken >> g) & 1u) == 0u;
-          if (free_slot && (best < 0 || ready[g] < bv)) {
+          if (free_slot && (best < 0 || rd[g] < bv)) {
             best = g;
-            bv = ready[g];
+            bv = rd[g];
           }
         }
         taken |= 1u << best;
@@ -342,12 +348,11 @@ __global__ void __launch_bounds__(128) k_eval_full(const FullArgs a) {
       }
       const float hold = (INT && isfinite(rt)) ? ceilf(rt) : rt;
       const float nxt = s + hold;
-#pragma unroll
       for (int g = 0; g < kSlots; ++g)
-        if ((taken >> g) & 1u) ready[g] = nxt;
+        if ((taken >> g) & 1u) rd[g] = nxt;
       mk = fmaxf(mk, s + rt);
       if (a.start) a.start[b * a.J + j] = s;
-      if (a.slotmask) a.slotmask[b * a.J + j] = taken;
+      if (a.slotmask) a.slotmask[b * a.J + j] = (static_cast<uint32_t>(node) << 16) | taken;
     }
     if (a.out) a.out[b] = mk;
   }
@@ -355,8 +360,9 @@ __global__ void __launch_bounds__(128) k_eval_full(const FullArgs a) {
 
 // ------------------------------------------------------------------------------------------
 // validation of external candidates: prio rows are permutations of 0..J-1 and every opt byte
-// names an existing (finite) table cell.  bad[0] counts offending rows.
-__global__ void k_validate(const float* tab, int J, int SG, const uint8_t* opt, const uint8_t* prio, int pb,
+// names an existing (finite) table cell (and, with several nodes, an existing node).
+// bad[0] counts offending rows.
+__global__ void k_validate(const float* tab, int J, int SG, int nodes, const uint8_t* opt, const uint8_t* prio, int pb,
                            long long B, long long stride_o, long long stride_p, unsigned long long* bad) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -378,7 +384,11 @@ __global__ void k_validate(const float* tab, int J, int SG, const uint8_t* opt, 
         const uint32_t old = atomicOr(&seen[j >> 5], 1u << (j & 31));
         if (old & (1u << (j & 31))) ok = false;
       }
-      const int o = orow[i];
+      int o = orow[i];
+      if (nodes > 1) {
+        if ((o >> 3) >= nodes) ok = false;
+        o &= 7;
+      }
       if (o >= SG || !isfinite(tab[static_cast<size_t>(i) * SG + o])) ok = false;
     }
     ok = __all_sync(0xffffffffu, ok);
@@ -394,13 +404,14 @@ static int round_row(int bytes) {
   return r16 * 16;
 }
 
-int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, TilePlan* tp) {
+int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp) {
   tp->row_o = round_row(J);
   tp->row_p = round_row(J * pb);
   tp->copy_o = (J + 15) & ~15;
   tp->copy_p = (J * pb + 15) & ~15;
   const size_t tab_bytes = (static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15);
-  const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + (stream ? 0 : tp->row_p));
+  const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + (stream ? 0 : tp->row_p)) +
+                          (nodes > 1 ? static_cast<size_t>(nodes) * 1024u : 0u);
   int nw = stream ? 16 : 8;
   while (nw > 0 && tab_bytes + 16 * ((1 + nw + 1) / 2) + nw * per_warp > dev.smem_optin) --nw;
   tp->warps = nw;
@@ -408,9 +419,9 @@ int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, TilePlan* 
   return nw;
 }
 
-template <int PB, bool INT, bool STREAM>
+template <int PB, bool INT, bool STREAM, bool MULTI>
 static cudaError_t launch_tiles(const Device& dev, const TileArgs& a, const TilePlan& tp, cudaStream_t st) {
-  auto kern = k_eval_tiles<PB, INT, STREAM>;
+  auto kern = k_eval_tiles<PB, INT, STREAM, MULTI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
   if (e != cudaSuccess) return e;
   long long ctas = (a.ntiles + tp.warps - 1) / tp.warps;
@@ -420,15 +431,26 @@ static cudaError_t launch_tiles(const Device& dev, const TileArgs& a, const Tile
 }
 
 template <int PB, bool INT>
+static cudaError_t dispatch_tiles(const Device& dev, const TileArgs& a, const TilePlan& tp, bool stream, bool multi,
+                                  cudaStream_t st) {
+  if (stream) {
+    return multi ? launch_tiles<PB, INT, true, true>(dev, a, tp, st) : launch_tiles<PB, INT, true, false>(dev, a, tp, st);
+  }
+  return multi ? launch_tiles<PB, INT, false, true>(dev, a, tp, st) : launch_tiles<PB, INT, false, false>(dev, a, tp, st);
+}
+
+template <int PB, bool INT, bool MULTI>
 static cudaError_t launch_generic(const Device& dev, const GenericArgs& a0, cudaStream_t st) {
   GenericArgs a = a0;
-  auto kern = k_eval_generic<PB, INT>;
-  size_t tab_bytes = static_cast<size_t>(a.J) * a.SG * 4;
-  size_t smem = 0;
+  auto kern = k_eval_generic<PB, INT, MULTI>;
+  const size_t tab_bytes = static_cast<size_t>(a.J) * a.SG * 4;
+  size_t smem = MULTI ? static_cast<size_t>(4) * a.nodes * 1024u : 0u;  // 4 warps per CTA
   a.tab_in_smem = 0;
   if (tab_bytes <= dev.smem_optin / 2) {
     a.tab_in_smem = 1;
-    smem = tab_bytes;
+    smem += tab_bytes;
+  }
+  if (smem > 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
@@ -444,6 +466,7 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
   if (c.B <= 0) return cudaSuccess;
   const int pb = c.J <= 256 ? 1 : 2;
   const bool ints = (c.flags & SB_FLAG_INTEGER_STARTS) != 0;
+  const bool multi = c.nodes > 1;
   const bool bulk_ok = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0);
   const bool stream_ok = bulk_ok && (c.stride_p % 32 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 32 == 0) &&
@@ -453,10 +476,10 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
   bool stream = false;
   if (!c.force_generic) {
     if (stream_ok) {
-      nw = plan_tiles(dev, c.J, c.SG, pb, true, &tp);
+      nw = plan_tiles(dev, c.J, c.SG, pb, true, c.nodes, &tp);
       stream = nw >= 2 && c.stride_o >= tp.copy_o && c.stride_p >= ((c.J * pb + 31) & ~31);
     }
-    if (!stream) nw = plan_tiles(dev, c.J, c.SG, pb, false, &tp);
+    if (!stream) nw = plan_tiles(dev, c.J, c.SG, pb, false, c.nodes, &tp);
   }
   if (nw >= 2) {
     TileArgs a;
@@ -464,24 +487,25 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
     a.stride_o = c.stride_o; a.stride_p = c.stride_p;
     a.row_o = tp.row_o; a.row_p = tp.row_p; a.copy_o = tp.copy_o; a.copy_p = tp.copy_p;
     a.use_bulk = stream || (bulk_ok && (c.stride_o >= tp.copy_o) && (c.stride_p >= tp.copy_p));
+    a.nodes = c.nodes;
     a.out = c.out; a.best_key = c.best_key; a.id_base = c.id_base;
     a.ntiles = (c.B + 31) / 32;
     a.one = 1;
     if (path_used) *path_used = stream ? 3 : (a.use_bulk ? 2 : 1);
-    if (stream) {
-      if (pb == 1) return ints ? launch_tiles<1, true, true>(dev, a, tp, st) : launch_tiles<1, false, true>(dev, a, tp, st);
-      return ints ? launch_tiles<2, true, true>(dev, a, tp, st) : launch_tiles<2, false, true>(dev, a, tp, st);
-    }
-    if (pb == 1) return ints ? launch_tiles<1, true, false>(dev, a, tp, st) : launch_tiles<1, false, false>(dev, a, tp, st);
-    return ints ? launch_tiles<2, true, false>(dev, a, tp, st) : launch_tiles<2, false, false>(dev, a, tp, st);
+    if (pb == 1) return ints ? dispatch_tiles<1, true>(dev, a, tp, stream, multi, st) : dispatch_tiles<1, false>(dev, a, tp, stream, multi, st);
+    return ints ? dispatch_tiles<2, true>(dev, a, tp, stream, multi, st) : dispatch_tiles<2, false>(dev, a, tp, stream, multi, st);
   }
   GenericArgs g;
   g.tab = c.tab; g.J = c.J; g.SG = c.SG; g.opt = c.opt; g.prio = c.prio; g.B = c.B;
   g.stride_o = c.stride_o; g.stride_p = c.stride_p; g.out = c.out; g.best_key = c.best_key;
-  g.id_base = c.id_base; g.tab_in_smem = 0; g.one = 1;
+  g.id_base = c.id_base; g.tab_in_smem = 0; g.nodes = c.nodes; g.one = 1;
   if (path_used) *path_used = 0;
-  if (pb == 1) return ints ? launch_generic<1, true>(dev, g, st) : launch_generic<1, false>(dev, g, st);
-  return ints ? launch_generic<2, true>(dev, g, st) : launch_generic<2, false>(dev, g, st);
+  if (multi) {
+    if (pb == 1) return ints ? launch_generic<1, true, true>(dev, g, st) : launch_generic<1, false, true>(dev, g, st);
+    return ints ? launch_generic<2, true, true>(dev, g, st) : launch_generic<2, false, true>(dev, g, st);
+  }
+  if (pb == 1) return ints ? launch_generic<1, true, false>(dev, g, st) : launch_generic<1, false, false>(dev, g, st);
+  return ints ? launch_generic<2, true, false>(dev, g, st) : launch_generic<2, false, false>(dev, g, st);
 }
 
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st) {
@@ -490,7 +514,8 @@ cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start,
   const bool ints = (c.flags & SB_FLAG_INTEGER_STARTS) != 0;
   FullArgs a;
   a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
-  a.stride_o = c.stride_o; a.stride_p = c.stride_p; a.out = c.out; a.start = start; a.slotmask = slotmask;
+  a.stride_o = c.stride_o; a.stride_p = c.stride_p; a.nodes = c.nodes < 1 ? 1 : c.nodes;
+  a.out = c.out; a.start = start; a.slotmask = slotmask;
   long long blocks = (c.B + 127) / 128;
   long long cap = static_cast<long long>(dev.sm_count) * 16;
   int grid = static_cast<int>(blocks < cap ? blocks : cap);
@@ -513,7 +538,7 @@ cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long 
   long long blocks = (c.B + 3) / 4;
   long long cap = static_cast<long long>(dev.sm_count) * 8;
   int grid = static_cast<int>(blocks < cap ? blocks : cap);
-  k_validate<<<grid, threads, smem, st>>>(c.tab, c.J, c.SG, c.opt, c.prio, pb, c.B, c.stride_o, c.stride_p, bad);
+  k_validate<<<grid, threads, smem, st>>>(c.tab, c.J, c.SG, c.nodes, c.opt, c.prio, pb, c.B, c.stride_o, c.stride_p, bad);
   return cudaGetLastError();
 }
 

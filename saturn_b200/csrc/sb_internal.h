@@ -27,13 +27,14 @@ struct EvalCall {
   long long B = 0;
   long long stride_o = 0, stride_p = 0;  // bytes
   unsigned flags = 0;
+  int nodes = 1;  // > 1: multi-node (reduced table, opt = (node << 3) | (k - 1))
   float* out = nullptr;
   unsigned long long* best_key = nullptr;
   uint32_t id_base = 0;
   int force_generic = 0;
 };
 
-int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, TilePlan* tp);
+int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp);
 cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used);
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st);
 cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st);

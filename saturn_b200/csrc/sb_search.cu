@@ -39,7 +39,9 @@ __global__ void k_init_population(SearchDev s) {
   const uint64_t gid = s.chain_base + static_cast<uint64_t>(c);
   for (int j = 0; j < s.J; ++j) {
     const uint64_t r = rng_u64(s.seed, gid, 0x100000000ull + j);
-    orow[j] = s.vopt[j * kSlots + bounded(r, s.nvalid[j])];
+    uint8_t ob = s.vopt[j * kSlots + bounded(r, s.nvalid[j])];
+    if (s.nodes > 1) ob = static_cast<uint8_t>((ob & 7) | (bounded(rng_u64(s.seed, gid, 0x300000000ull + j), s.nodes) << 3));
+    orow[j] = ob;
     prio_st<PB>(prow, j, j);
   }
   for (int i = s.J - 1; i > 0; --i) {
@@ -76,17 +78,30 @@ __global__ void k_propose(SearchDev s, int round) {
   const uint64_t r2 = rng_u64(s.seed, gid, 4ull * round + 2);
   const uint32_t kind = bounded(r0, 100);
   const int J = s.J;
+  if (s.nodes > 1 && kind >= 85) {
+    // move one job to another node (milp.py:117-137: exactly one node per task)
+    if (lane == 0) {
+      const int j = bounded(r1, J);
+      const uint8_t curv = co[j];
+      int nn = bounded(r2, s.nodes - 1);
+      if (nn >= (curv >> 3)) ++nn;
+      po[j] = static_cast<uint8_t>((curv & 7) | (nn << 3));
+    }
+    return;
+  }
   if (kind < 30) {
-    // change one job's option
+    // change one job's option (keeping its node)
     const int j = bounded(r1, J);
     const int n = s.nvalid[j];
     if (n > 1) {
       if (lane == 0) {
         int pick = bounded(r2, n - 1);
         const uint8_t curv = co[j];
+        const uint8_t node_bits = s.nodes > 1 ? (curv & 0xf8) : 0;
+        const uint8_t cur_opt = s.nodes > 1 ? (curv & 7) : curv;
         uint8_t nv = s.vopt[j * kSlots + pick];
-        if (nv == curv) nv = s.vopt[j * kSlots + n - 1];
-        po[j] = nv;
+        if (nv == cur_opt) nv = s.vopt[j * kSlots + n - 1];
+        po[j] = nv | node_bits;
       }
       return;
     }

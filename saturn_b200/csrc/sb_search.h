@@ -6,6 +6,7 @@ namespace sb {
 
 struct SearchDev {
   int J = 0, pb = 1;
+  int nodes = 1;  // > 1: opt bytes carry the node in bits 3..
   long long chains = 0;
   uint64_t chain_base = 0;
   uint64_t seed = 0;

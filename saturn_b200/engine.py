@@ -44,6 +44,7 @@ class Engine:
         self.S = 0
         self.G = 0
         self.gcount = None
+        self.nodes = 1
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -61,9 +62,10 @@ class Engine:
         check(self._lib.sb_sync(self._h))
 
     # ------------------------------------------------------------------ table
-    def set_table(self, T, gcount: Optional[Sequence[int]] = None, sentinel: Optional[float] = None):
+    def set_table(self, T, gcount: Optional[Sequence[int]] = None, sentinel: Optional[float] = None, nodes: int = 1):
         """T[J][S][G] fp32 (numpy array or torch tensor, host or device); gcount[G] GPU counts.
-        `sentinel`: cells at/above it are never proposed by the search (default 1e6)."""
+        `sentinel`: cells at/above it are never proposed by the search (default 1e6).
+        `nodes` > 1: candidates are evaluated with reduced=True and opt = (node << 3) | (k - 1)."""
         if sentinel is not None:
             check(self._lib.sb_set_sentinel(self._h, C.c_float(sentinel)))
         if isinstance(T, torch.Tensor):
@@ -81,10 +83,11 @@ class Engine:
         gc = np.ascontiguousarray(gcount, dtype=np.uint8)
         if gc.shape != (G,):
             raise ValueError("gcount must have %d entries" % G)
-        check(self._lib.sb_set_table(self._h, C.c_void_p(ptr), C.c_void_p(gc.ctypes.data), J, S, G, 1))
+        check(self._lib.sb_set_table(self._h, C.c_void_p(ptr), C.c_void_p(gc.ctypes.data), J, S, G, int(nodes)))
         del keep
         self.J, self.S, self.G = int(J), int(S), int(G)
         self.gcount = [int(x) for x in gc]
+        self.nodes = int(nodes)
         return self
 
     def reduced_table(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -173,12 +176,14 @@ class Engine:
         mask = np.empty(J, dtype=np.uint32)
         strat = np.empty(J, dtype=np.uint8)
         gpus = np.empty(J, dtype=np.uint8)
+        node = np.empty(J, dtype=np.uint8)
         mk = C.c_float(0)
         check(self._lib.sb_decode(self._h, C.c_void_p(opt.ctypes.data), C.c_void_p(prio.ctypes.data),
                                   _flags(integer_starts, reduced), C.c_void_p(start.ctypes.data),
                                   C.c_void_p(mask.ctypes.data), C.c_void_p(strat.ctypes.data),
-                                  C.c_void_p(gpus.ctypes.data), C.byref(mk)))
-        return {"start": start, "slotmask": mask, "strategy": strat, "gpus": gpus, "makespan": float(mk.value)}
+                                  C.c_void_p(gpus.ctypes.data), C.c_void_p(node.ctypes.data), C.byref(mk)))
+        return {"start": start, "slotmask": mask, "strategy": strat, "gpus": gpus, "node": node,
+                "makespan": float(mk.value)}
 
     # ------------------------------------------------------------------ search
     def search_init(self, chains: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
@@ -259,8 +264,10 @@ def padded_rows(B: int, J: int, dtype: torch.dtype, device, pinned: bool = False
 
 
 def random_candidates(engine: Engine, B: int, valid: np.ndarray, seed: int = 0, gcount=None, device=None,
-                      pinned: bool = False):
-    """opt ~ U{valid cells of each job}, prio = random permutations (torch RNG on `device`)."""
+                      pinned: bool = False, nodes: int = 1):
+    """opt ~ U{valid cells of each job}, prio = random permutations (torch RNG on `device`).
+    nodes > 1: `valid` must describe the reduced table (S = 1); a uniform node index is OR-ed into
+    bits 3.. of every opt byte."""
     J = engine.J
     device = engine.device if device is None else torch.device(device)
     gen_dev = device if device.type == "cuda" else torch.device("cpu")
@@ -287,6 +294,9 @@ def random_candidates(engine: Engine, B: int, valid: np.ndarray, seed: int = 0, 
         o = torch.gather(cells_t[None, :, :].expand(nb, -1, -1), 2, pick[:, :, None])[:, :, 0]
         keys = torch.rand((nb, J), generator=g, device=gen_dev)
         p = torch.argsort(keys, dim=1)
+        if nodes > 1:
+            nd = torch.randint(0, nodes, (nb, J), generator=g, device=gen_dev, dtype=torch.uint8)
+            o = o | (nd << 3)
         opt[b0:b0 + nb].copy_(o)
         if engine.prio_dtype == torch.uint8:
             prio[b0:b0 + nb].copy_(p.to(torch.uint8))

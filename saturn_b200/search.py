@@ -43,9 +43,11 @@ def key_makespan(key: int) -> float:
     return float(np.array([(key >> 32) & 0xffffffff], dtype=np.uint32).view(np.float32)[0])
 
 
-def lpt_seeds(tmin: np.ndarray, sentinel: float = 1.0e6):
-    """Heuristic warm candidates in the reduced encoding (opt byte = k-1), longest-processing-time
-    order: (a) every job on its fastest option, (b) every job on its least GPU-seconds option."""
+def lpt_seeds(tmin: np.ndarray, sentinel: float = 1.0e6, nodes: int = 1):
+    """Heuristic warm candidates in the reduced encoding (opt byte = k-1, plus node << 3 when there
+    are several nodes), longest-processing-time order: (a) every job on its fastest option,
+    (b) every job on its least GPU-seconds option, (c) in between.  Nodes are filled greedily by
+    accumulated GPU-seconds."""
     J = tmin.shape[0]
     usable = np.where(tmin < sentinel, tmin, np.inf)
     if not np.isfinite(usable).any(axis=1).all():
@@ -57,7 +59,15 @@ def lpt_seeds(tmin: np.ndarray, sentinel: float = 1.0e6):
         col = np.argmin(cost, axis=1)
         rt = usable[np.arange(J), col]
         order = np.argsort(-rt * (col + 1) ** 0.5, kind="stable")
-        seeds.append((col.astype(np.uint8), order))
+        ob = col.astype(np.uint8)
+        if nodes > 1:
+            load = np.zeros(nodes)
+            ob = ob.copy()
+            for j in order:
+                n = int(np.argmin(load))
+                load[n] += float(rt[j]) * (int(col[j]) + 1)
+                ob[j] |= n << 3
+        seeds.append((ob, order))
     return seeds
 
 
@@ -81,8 +91,9 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
         # the rest stays random (diversity), tournament resampling then concentrates the population
         tmin, args = engine.reduced_table()
         per = max(1, chains // 8)
-        for i, (col, order) in enumerate(lpt_seeds(tmin)):
-            opt = col if reduced else ((args[np.arange(J), col].astype(np.uint8) << 3) | col)
+        nodes = getattr(engine, "nodes", 1)
+        for i, (col, order) in enumerate(lpt_seeds(tmin, nodes=nodes)):
+            opt = col if reduced else ((args[np.arange(J), col & 7].astype(np.uint8) << 3) | col)
             first = min(i * per, max(0, chains - per))
             engine.search_inject(opt.astype(np.uint8), order.astype(pdt), copies=min(per, chains), first=first)
     local_key = engine.search_best_key()          # aliases device memory

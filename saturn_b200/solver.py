@@ -86,7 +86,8 @@ def build_table(task_list):
 
 # ------------------------------------------------------------------------------------------ outputs
 def plan_to_arrays(n_options: Sequence[int], opt_index: Sequence[int], start: Sequence[float],
-                   slotmask: Sequence[int], position: Sequence[int], nodes: int = 1):
+                   slotmask: Sequence[int], position: Sequence[int], nodes: int = 1,
+                   node_of: Optional[Sequence[int]] = None):
     """(start, GPU mask, chosen option, schedule position) per task -> the reference's arrays.
 
     Layout and meaning follow milp.py:330-352: sta[N][G][J] start times (0 where the task does
@@ -99,15 +100,17 @@ def plan_to_arrays(n_options: Sequence[int], opt_index: Sequence[int], start: Se
     sta = [[[0.0] * J for _ in range(NSLOT)] for _ in range(nodes)]
     tga = [[[0.0] * NSLOT for _ in range(nodes)] for _ in range(J)]
     bss = [[0.0] * int(n_options[t]) for t in range(J)]
-    bna = [[1.0] + [0.0] * (nodes - 1) for _ in range(J)]
+    bna = [[0.0] * nodes for _ in range(J)]
     for t in range(J):
         bss[t][int(opt_index[t])] = 1.0
+        n = int(node_of[t]) if node_of is not None else 0
+        bna[t][n] = 1.0
         m = int(slotmask[t])
         s = float(start[t])
         for g in range(NSLOT):
             if (m >> g) & 1:
-                tga[t][0][g] = 1.0
-                sta[0][g][t] = s
+                tga[t][n][g] = 1.0
+                sta[n][g][t] = s
     pos = np.asarray(position)
     before = (pos[:, None] < pos[None, :]).astype(np.float64)
     boa = before.tolist()
@@ -116,7 +119,7 @@ def plan_to_arrays(n_options: Sequence[int], opt_index: Sequence[int], start: Se
     return sta, tga, bss, bna, boa
 
 
-def candidate_from_arrays(task_list, presolved):
+def candidate_from_arrays(task_list, presolved, nodes: int = 1):
     """Warm start: turn a previous plan (the `presolved` tuple) back into a candidate
     (reduced opt bytes, priority order) — the role of setInitialValue at milp.py:103-104,151-155,197-202."""
     if presolved is None:
@@ -135,8 +138,10 @@ def candidate_from_arrays(task_list, presolved):
             k = int(keys[int(np.argmax(bss[t]))])
             if not 1 <= k <= NSLOT:
                 return None
-            opt[t] = k - 1
             n = int(np.argmax(bna[t]))
+            if n >= nodes:
+                return None
+            opt[t] = (k - 1) | ((n << 3) if nodes > 1 else 0)
             gl = [g for g, v in enumerate(tga[t][n]) if v is not None and round(v) == 1]
             starts[t] = sta[n][gl[0]][t] if gl else 0.0
         order = np.argsort(starts, kind="stable")
@@ -158,15 +163,33 @@ def _engine():
     return _ENGINE
 
 
+def _default_nodes() -> int:
+    env = os.environ.get("SATURN_B200_NODES")
+    if env:
+        return max(1, int(env))
+    ray = __import__("sys").modules.get("ray")      # never import Ray just to ask
+    try:
+        if ray is not None and ray.is_initialized():
+            return max(1, len(ray.nodes()))
+    except Exception:
+        pass
+    return 1
+
+
 def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count() or 4) // 4), interval=1000,
           timeout=500, *, chains: Optional[int] = None, rounds: Optional[int] = None, seed: int = 0,
-          integer_starts: bool = True, engine=None, hysteresis: Optional[bool] = None):
+          integer_starts: bool = True, engine=None, hysteresis: Optional[bool] = None,
+          nodes: Optional[int] = None):
     """Drop-in for saturn.solver.solve (milp.py:23).
 
     Returns (sta, tga, bss, bna, boa, makespan) — milp.py:445 — with a real float makespan
     (the reference returns None on a cold start, milp.py:394-399; callers only thread it back in
     as `presolved`).  Keyword-only extras tune the GPU search; environment overrides:
     SATURN_B200_CHAINS, SATURN_B200_ROUNDS, SATURN_B200_BUDGET_S, SATURN_B200_HYSTERESIS.
+
+    Nodes.  The reference plans over len(ray.nodes()) nodes of 8 GPUs each (milp.py:58-62); here the
+    node count is the `nodes` keyword, else SATURN_B200_NODES, else an initialised Ray's node count,
+    else 1.  A task runs on exactly one node (milp.py:117-137).
 
     Re-planning policy.  As shipped, the reference ALWAYS adopts the fresh plan: its comparator
     (milp.py:383-442) keys on `saved_makespan`, which stays None from the cold start on
@@ -189,7 +212,10 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     for j in range(J):
         if usable[j].any():
             Tdev[j, 0, ~usable[j]] = np.inf
-    eng.set_table(Tdev, list(range(1, NSLOT + 1)), sentinel=float("inf"))
+    if nodes is None:
+        nodes = _default_nodes()
+    nodes = int(nodes)
+    eng.set_table(Tdev, list(range(1, NSLOT + 1)), sentinel=float("inf"), nodes=nodes)
     if chains is None:
         chains = int(os.environ.get("SATURN_B200_CHAINS", 1 << 16))
     if rounds is None:
@@ -199,7 +225,7 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
         budget = min(budget, float(timeout))
     except (TypeError, ValueError):
         pass
-    warm = candidate_from_arrays(task_list, presolved)
+    warm = candidate_from_arrays(task_list, presolved, nodes)
     res = run_search(eng, chains=chains, rounds=rounds, seed=seed, integer_starts=integer_starts, reduced=True,
                      time_budget_s=budget, patience=max(40, rounds // 4), warm=warm)
     dec = eng.decode(res.opt, res.prio, integer_starts=integer_starts, reduced=True)
@@ -210,7 +236,8 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     position = np.empty(J, dtype=np.int64)
     position[res.prio.astype(np.int64)] = np.arange(J)
     n_options = [len(t.strategies) for t in task_list]
-    prop = plan_to_arrays(n_options, chosen, dec["start"], dec["slotmask"], position)
+    prop = plan_to_arrays(n_options, chosen, dec["start"], dec["slotmask"], position, nodes=nodes,
+                          node_of=dec["node"])
     # the makespan the caller sees is recomputed in float64 from the emitted plan and the tasks'
     # own (un-rounded) runtimes: max_t start_t + runtime_t  (milp.py:170-177)
     rts = [list(t.strategies.values())[int(chosen[i])].runtime for i, t in enumerate(task_list)]
@@ -219,6 +246,7 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     global last_stats
     last_stats = {"candidates": res.evaluated, "rounds": res.rounds, "search_wall_s": res.wall_s,
                   "device_makespan": res.makespan, "makespan": prop_makespan, "J": J, "chains": chains,
+                  "nodes": nodes,
                   "total_wall_s": None, "adopted": True}
 
     # ---- introspection hysteresis (opt-in): the documented intent of milp.py:363-442

@@ -38,6 +38,14 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_n2():
+    import json
+    p = os.path.join(ROOT, "tests", "golden", "milp_cases_n2.json")
+    with open(p) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def engine():
     import torch
     from saturn_b200.engine import Engine

@@ -246,3 +246,33 @@ def test_full_size_properties(engine):
     sl = slice(500_000, 520_000)
     ref = c_oracle.evaluate(tab, opt[sl].cpu().numpy(), prio[sl].cpu().numpy(), True, np.float32, threads=8)
     assert np.array_equal(a_int[sl].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("J,nodes,B", [(64, 2, 6000), (100, 3, 3001), (256, 2, 4000), (300, 4, 700)])
+@pytest.mark.parametrize("ints", [True, False])
+def test_multi_node_parity(engine, J, nodes, B, ints):
+    """Several nodes (gangs confined to one node, milp.py:117-137): every kernel path == the oracle,
+    bit for bit, including start times and (node, GPU-mask) per job."""
+    T, valid = R.synth_table(J, 1, 8, seed=J, masked=False)
+    engine.set_table(T, nodes=nodes)
+    tab = R.canon_table(T, range(1, 9))
+    opt, prio = random_candidates(engine, B, valid, seed=4, nodes=nodes)
+    assert int((opt >> 3).max()) == nodes - 1 and engine.validate(opt, prio, reduced=True) == 0
+    with pytest.raises(Exception):
+        engine.eval(opt, prio, reduced=False)                   # multi-node needs the reduced table
+    a = engine.eval(opt, prio, integer_starts=ints, reduced=True)
+    assert engine.last_eval_path() == 3
+    pnp = prio.cpu().numpy()
+    ref, rstart, rmask = c_oracle.evaluate(tab, opt.cpu().numpy(), pnp, ints, np.float32, want_plan=True, threads=8,
+                                           nodes=nodes)
+    assert np.array_equal(a.cpu().numpy(), ref)
+    assert torch.equal(a, engine.eval(opt, prio, integer_starts=ints, reduced=True, _no_stream=True))
+    assert torch.equal(a, engine.eval(opt, prio, integer_starts=ints, reduced=True, _force_generic=True))
+    assert torch.equal(a, engine.eval(opt.contiguous(), prio.contiguous(), integer_starts=ints, reduced=True))
+    mk, start, mask = engine.eval_full(opt, prio, integer_starts=ints, reduced=True)
+    assert np.array_equal(mk.cpu().numpy(), ref) and np.array_equal(start.cpu().numpy(), rstart)
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint32), rmask)
+    bad = padded_rows(B, J, torch.uint8, engine.device)
+    bad.copy_(opt)
+    bad[5, 2] = (nodes << 3) | 1                                  # a node that does not exist
+    assert engine.validate(bad, prio, reduced=True) == 1

@@ -123,3 +123,21 @@ def test_orchestrate_simulated_run():
                        solver_kwargs={"chains": 4096, "rounds": 25}, max_intervals=50)
     assert all(t.total_batches == 0 for t in tasks)
     assert len(recs) >= 2 and sum(launched) >= 8
+
+
+def test_multi_node_solve_matches_reference_milp(golden_n2):
+    """solve(nodes=2) on the instances the reference MILP solved with ray.nodes() == 2 nodes."""
+    import saturn.solver as ss
+    for rec in golden_n2["cases"]:
+        tasks = tasks_from_tuples(rec["gpu_time_tuples"])
+        out = ss.solve(tasks, None, gurobi=False, timeout=60, chains=8192, rounds=60, nodes=2)
+        sta, tga, bss, bna, boa, mk = out
+        assert len(sta) == 2 and len(bna[0]) == 2
+        tuples = [[(g, s.runtime) for g, s in t.strategies.items()] for t in tasks]
+        assert R.milp_constraints_hold(tuples, sta, tga, bss, bna, boa, mk) == []
+        assert mk == pytest.approx(rec["makespan"], rel=1e-9), rec["name"]
+        npt, tdd, st = ss.convert_into_comprehensible(tasks, bss, boa, tga, bna, sta)
+        assert set(int(npt[t]) for t in tasks) == {0, 1}
+        # warm start from the previous plan keeps working with nodes
+        again = ss.solve(tasks, out, gurobi=False, timeout=60, chains=4096, rounds=20, nodes=2)
+        assert again[5] <= mk * (1 + 1e-9)

@@ -176,3 +176,26 @@ def test_product_and_oracle_generate_the_same_workload():
         a, va = synth_table(J, S, G, seed)
         b, vb = R.synth_table(J, S, G, seed)
         assert np.array_equal(a, b) and np.array_equal(va, vb)
+
+
+def test_multi_node_plan_arrays_and_decoder(golden_n2):
+    # emission: two nodes, tasks 0,1 on node 0 and task 2 on node 1
+    tuples = [[(8, 100.0)], [(4, 30.5), (8, 20.0)], [(8, 70.0)]]
+    tasks = tasks_from_tuples(tuples)
+    sta, tga, bss, bna, boa = plan_to_arrays([1, 2, 1], [0, 0, 0], [0.0, 100.0, 0.0], [0xff, 0x0f, 0xff], [0, 2, 1],
+                                             nodes=2, node_of=[0, 0, 1])
+    assert len(sta) == 2 and bna == [[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]
+    assert R.milp_constraints_hold(tuples, sta, tga, bss, bna, boa, 130.5) == []
+    npt, tdd, st = convert_into_comprehensible(tasks, bss, boa, tga, bna, sta)
+    assert [int(npt[t]) for t in tasks] == [0, 0, 1] and st == [0.0, 100.0, 0.0]
+    assert tdd[tasks[1]] == [tasks[0]] and tasks[2] not in tdd
+    warm = candidate_from_arrays(tasks, (sta, tga, bss, bna, boa, 130.5), nodes=2)
+    assert list(warm[0]) == [7, 3, 7 | 8]
+    # decoder parity on the arrays the reference MILP returned with 2 nodes
+    for rec in golden_n2["cases"]:
+        tasks = tasks_from_tuples(rec["gpu_time_tuples"])
+        npt, tdd, st = convert_into_comprehensible(tasks, rec["bss"], rec["boa"], rec["tga"], rec["bna"], rec["sta"])
+        d = rec["decoded"]
+        idx = {t: i for i, t in enumerate(tasks)}
+        assert [int(npt[t]) for t in tasks] == d["node_per_task"] and [float(x) for x in st] == d["start"]
+        assert [sorted(idx[x] for x in tdd[t]) for t in tasks] == d["deps"]
