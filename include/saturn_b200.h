@@ -168,6 +168,10 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
 /* tournament resampling: every chain continues from a random rival's candidate if the rival's
  * current makespan is strictly better (keeps the population concentrated on good basins) */
 int sb_search_resample(sb_handle* h);
+/* 1 if rounds run as ONE fused kernel (move + evaluate + accept on shared-memory rows; needs both rows
+ * of 32 candidates x >= 4 warps to fit beside the table), 0 if they run as propose / evaluate / accept
+ * kernels (large J).  Both are the same Metropolis search; moves and RNG streams differ slightly. */
+int sb_search_is_fused(sb_handle* h);
 /* candidates evaluated so far by this handle's searches */
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);
 

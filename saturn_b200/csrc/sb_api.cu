@@ -39,6 +39,7 @@ struct SearchState {
   float scale = 0.f;  // temperature unit: incumbent makespan after initialisation
   long long evaluated = 0;
   int rounds_done = 0;
+  bool fused_ok = true;  // run rounds with the fused kernel while its tiles fit
   uint8_t *cand_o = nullptr, *cand_p = nullptr;  // device scratch for injected candidates
   void* blocks[16];
   int nblocks = 0;
@@ -491,6 +492,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   s.scale = isfinite(mk) ? mk : 1.0f;
   s.evaluated = d.chains;
   s.rounds_done = 0;
+  s.fused_ok = !(p->flags & 0x20000000u) && search_round_fits(h->dev, J, (reduced ? 1 : h->S) * kSlots, h->nodes);
   return SB_OK;
 }
 
@@ -508,10 +510,34 @@ int sb_search_round(sb_handle* h, int rounds) {
     else if (s.p.t_end <= 0.f) tf = s.p.t_start * (1.f - frac);
     else tf = s.p.t_start * powf(s.p.t_end / s.p.t_start, frac);
     const float temperature = tf * s.scale;
-    CK(search_propose(s.d, round, h->stream));
-    if ((rc = search_eval(h, false, 0, s.d.chains))) return rc;
-    CK(search_keep_best(s.d, false, h->stream));
-    CK(search_accept(s.d, round, temperature, h->stream));
+    bool fused = false;
+    if (s.fused_ok) {
+      EvalCall c;
+      if ((rc = make_call(h, s.d.cur_o, s.d.cur_p, s.d.chains, s.d.stride_o, s.p.flags, &c))) return rc;
+      c.best_key = s.d.keys;
+      c.id_base = static_cast<uint32_t>(s.d.chain_base);
+      SearchFuse sf;
+      sf.cur_mk = s.d.cur_mk; sf.cur_o = s.d.cur_o; sf.cur_p = s.d.cur_p;
+      sf.vopt = s.d.vopt; sf.nvalid = s.d.nvalid;
+      sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
+      sf.temperature = temperature;
+      cudaError_t e = search_round_launch(h->dev, c, sf, h->stream);
+      if (e == cudaSuccess) {
+        fused = true;
+        CK(search_keep_best(s.d, true, h->stream));   // an improving proposal is always accepted: it is in cur
+      } else if (e != cudaErrorNotSupported) {
+        return fail(SB_ERR_CUDA, "fused search round failed: %s", cudaGetErrorString(e));
+      } else {
+        cudaGetLastError();
+        s.fused_ok = false;
+      }
+    }
+    if (!fused) {
+      CK(search_propose(s.d, round, h->stream));
+      if ((rc = search_eval(h, false, 0, s.d.chains))) return rc;
+      CK(search_keep_best(s.d, false, h->stream));
+      CK(search_accept(s.d, round, temperature, h->stream));
+    }
     s.rounds_done = round;
     s.evaluated += s.d.chains;
   }
@@ -577,6 +603,8 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
   s.evaluated += copies;
   return SB_OK;
 }
+
+int sb_search_is_fused(sb_handle* h) { return (h && h->search.ready && h->search.fused_ok) ? 1 : 0; }
 
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done) {
   if (!h) return fail(SB_ERR_ARG, "null handle");

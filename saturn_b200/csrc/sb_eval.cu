@@ -45,6 +45,7 @@ struct TileArgs {
   uint32_t id_base;
   long long ntiles;
   int one;  // run-time 1 (see pmov_fma)
+  SearchFuse sf;  // SEARCH variant only
 };
 
 struct PrioChunk {
@@ -115,8 +116,113 @@ __device__ __forceinline__ void fold_best(unsigned long long* best_key, bool act
   }
 }
 
-template <int PB, bool INT, bool STREAM, bool MULTI>
+// ---- SEARCH variant: one Metropolis round fused into the tile kernel.  The rows a warp fetched
+// are the chains' CURRENT candidates; every lane applies its own random move to its private
+// shared-memory rows, scores the result, decides acceptance and — only when accepted — writes the
+// few changed bytes back to the chain's rows in HBM.  No proposal buffer, no separate propose /
+// accept kernels (they cost 60 % of an unfused round at 1 M chains, profiles/r01_search_round.md).
+struct Move {
+  int kind;  // 0 none, 1 opt byte of job a changed, 2 positions a,b swapped, 3 positions [a..b] rewritten
+  int a, b;
+};
+
+__device__ __forceinline__ uint32_t bounded32(uint64_t r, uint32_t n) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(r >> 32)) * n) >> 32);
+}
+
+template <int PB>
+__device__ __forceinline__ int smem_prio_ld(const uint8_t* row, int i) {
+  return PB == 1 ? row[i] : reinterpret_cast<const uint16_t*>(row)[i];
+}
+template <int PB>
+__device__ __forceinline__ void smem_prio_st(uint8_t* row, int i, int v) {
+  if (PB == 1) row[i] = static_cast<uint8_t>(v);
+  else reinterpret_cast<uint16_t*>(row)[i] = static_cast<uint16_t>(v);
+}
+
+template <int PB>
+__device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t gid, uint8_t* orow, uint8_t* prow) {
+  Move m;
+  m.kind = 0; m.a = 0; m.b = 0;
+  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * sf.round + 0);
+  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * sf.round + 1);
+  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * sf.round + 2);
+  const uint32_t kind = bounded32(r0, 100);
+  if (sf.nodes > 1 && kind >= 85) {  // move one job to another node (milp.py:117-137)
+    const int j = bounded32(r1, J);
+    const uint8_t curv = orow[j];
+    int nn = bounded32(r2, sf.nodes - 1);
+    if (nn >= (curv >> 3)) ++nn;
+    orow[j] = static_cast<uint8_t>((curv & 7) | (nn << 3));
+    m.kind = 1; m.a = j;
+    return m;
+  }
+  if (kind < 30) {  // change one job's option (keeping its node)
+    const int j = bounded32(r1, J);
+    const int n = sf.nvalid[j];
+    if (n > 1) {
+      const int pick = bounded32(r2, n - 1);
+      const uint8_t curv = orow[j];
+      const uint8_t node_bits = sf.nodes > 1 ? (curv & 0xf8) : 0;
+      const uint8_t cur_opt = sf.nodes > 1 ? (curv & 7) : curv;
+      uint8_t nv = sf.vopt[j * kSlots + pick];
+      if (nv == cur_opt) nv = sf.vopt[j * kSlots + n - 1];
+      orow[j] = nv | node_bits;
+      m.kind = 1; m.a = j;
+      return m;
+    }
+  }
+  if (J < 2) return m;
+  const int a = bounded32(r1, J);
+  if (kind < 70) {  // swap two priorities
+    int b = bounded32(r2, J - 1);
+    if (b >= a) ++b;
+    const int va = smem_prio_ld<PB>(prow, a), vb = smem_prio_ld<PB>(prow, b);
+    smem_prio_st<PB>(prow, a, vb);
+    smem_prio_st<PB>(prow, b, va);
+    m.kind = 2; m.a = a; m.b = b;
+    return m;
+  }
+  // re-insert the job at position a up to 48 places earlier or later
+  const int span = J - 1 < 48 ? J - 1 : 48;
+  int d = 1 + static_cast<int>(bounded32(r2, 2 * span));  // 1..2*span
+  int b = d <= span ? a + d : a - (d - span);
+  if (b < 0) b = 0;
+  if (b > J - 1) b = J - 1;
+  if (b == a) return m;
+  const int va = smem_prio_ld<PB>(prow, a);
+  if (a < b) {
+    for (int i = a; i < b; ++i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i + 1));
+  } else {
+    for (int i = a; i > b; --i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i - 1));
+  }
+  smem_prio_st<PB>(prow, b, va);
+  m.kind = 3; m.a = a < b ? a : b; m.b = a < b ? b : a;
+  return m;
+}
+
+template <int PB>
+__device__ __forceinline__ void write_back(const Move& m, const uint8_t* orow, const uint8_t* prow, uint8_t* go,
+                                           uint8_t* gp) {
+  if (m.kind == 1) {
+    go[m.a] = orow[m.a];
+  } else if (m.kind == 2) {
+    if (PB == 1) { gp[m.a] = prow[m.a]; gp[m.b] = prow[m.b]; }
+    else {
+      reinterpret_cast<uint16_t*>(gp)[m.a] = reinterpret_cast<const uint16_t*>(prow)[m.a];
+      reinterpret_cast<uint16_t*>(gp)[m.b] = reinterpret_cast<const uint16_t*>(prow)[m.b];
+    }
+  } else if (m.kind == 3) {
+    for (int i = m.a; i <= m.b; ++i) {
+      if (PB == 1) gp[i] = prow[i];
+      else reinterpret_cast<uint16_t*>(gp)[i] = reinterpret_cast<const uint16_t*>(prow)[i];
+    }
+  }
+}
+
+template <int PB, bool INT, bool STREAM, bool MULTI, bool SEARCH = false>
 __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const TileArgs a) {
+  static_assert(!(SEARCH && STREAM), "the fused search round mutates shared-memory rows");
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,6 +300,11 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
     }
     // ---- one candidate per lane
     float mk = 0.f;
+    Move mv;
+    mv.kind = 0; mv.a = 0; mv.b = 0;
+    if (SEARCH && active)
+      mv = apply_move<PB>(a.sf, a.J, a.sf.chain_base + static_cast<uint64_t>(b0 + lane), tile_o + lane * a.row_o,
+                          tile_p + lane * a.row_p);
     if (active) {
       st.reset(a.nodes);
       const int J = a.J;
@@ -233,7 +344,23 @@ __global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const Tile
         }
       }
       mk = st.result();
-      a.out[b0 + lane] = mk;
+      if (!SEARCH) a.out[b0 + lane] = mk;
+    }
+    if (SEARCH && active) {
+      // Metropolis acceptance at this round's temperature; write back only what changed
+      const long long c = b0 + lane;
+      const float cm = a.sf.cur_mk[c];
+      bool acc = mk <= cm;
+      if (!acc && a.sf.temperature > 0.f && isfinite(mk)) {
+        const uint64_t r = rng_u64(a.sf.seed, a.sf.chain_base + static_cast<uint64_t>(c), 4ull * a.sf.round + 3);
+        const float u = (static_cast<uint32_t>(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
+        acc = u < __expf(-(mk - cm) / a.sf.temperature);
+      }
+      if (acc && mv.kind != 0) {
+        write_back<PB>(mv, tile_o + lane * a.row_o, tile_p + lane * a.row_p, a.sf.cur_o + c * a.stride_o,
+                       a.sf.cur_p + c * a.stride_p);
+        a.sf.cur_mk[c] = mk;
+      }
     }
     if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b0 + lane), lane);
   }
@@ -506,6 +633,52 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
   }
   if (pb == 1) return ints ? launch_generic<1, true, false>(dev, g, st) : launch_generic<1, false, false>(dev, g, st);
   return ints ? launch_generic<2, true, false>(dev, g, st) : launch_generic<2, false, false>(dev, g, st);
+}
+
+// One fused search round over `c.B` chains whose current candidates are (c.opt, c.prio).  Returns
+// cudaErrorNotSupported when the shared-memory tiles (both rows resident, >= 4 warps) do not fit;
+// the caller then runs the unfused propose / evaluate / accept round.
+template <int PB, bool INT>
+static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const TilePlan& tp, bool multi, cudaStream_t st) {
+  auto launch = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
+    if (e != cudaSuccess) return e;
+    long long ctas = (a.ntiles + tp.warps - 1) / tp.warps;
+    int grid = static_cast<int>(ctas < dev.sm_count ? ctas : dev.sm_count);
+    kern<<<grid, tp.warps * 32, tp.smem, st>>>(a);
+    return cudaGetLastError();
+  };
+  if (multi) return launch(k_eval_tiles<PB, INT, false, true, true>);
+  return launch(k_eval_tiles<PB, INT, false, false, true>);
+}
+
+bool search_round_fits(const Device& dev, int J, int SG, int nodes) {
+  const int pb = J <= 256 ? 1 : 2;
+  TilePlan tp;
+  return plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 4;
+}
+
+cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st) {
+  if (c.B <= 0) return cudaSuccess;
+  const int pb = c.J <= 256 ? 1 : 2;
+  const bool ints = (c.flags & SB_FLAG_INTEGER_STARTS) != 0;
+  const bool bulk_ok = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0);
+  TilePlan tp;
+  const int nw = plan_tiles(dev, c.J, c.SG, pb, false, c.nodes, &tp);
+  if (nw < 4 || !bulk_ok || c.stride_o < tp.copy_o || c.stride_p < tp.copy_p) return cudaErrorNotSupported;
+  TileArgs a;
+  a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
+  a.stride_o = c.stride_o; a.stride_p = c.stride_p;
+  a.row_o = tp.row_o; a.row_p = tp.row_p; a.copy_o = tp.copy_o; a.copy_p = tp.copy_p;
+  a.use_bulk = 1;
+  a.nodes = c.nodes;
+  a.out = nullptr; a.best_key = c.best_key; a.id_base = c.id_base;
+  a.ntiles = (c.B + 31) / 32;
+  a.one = 1;
+  a.sf = sf;
+  if (pb == 1) return ints ? dispatch_search<1, true>(dev, a, tp, c.nodes > 1, st) : dispatch_search<1, false>(dev, a, tp, c.nodes > 1, st);
+  return ints ? dispatch_search<2, true>(dev, a, tp, c.nodes > 1, st) : dispatch_search<2, false>(dev, a, tp, c.nodes > 1, st);
 }
 
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st) {

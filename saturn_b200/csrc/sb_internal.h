@@ -34,8 +34,23 @@ struct EvalCall {
   int force_generic = 0;
 };
 
+// what the fused search round needs besides an EvalCall (see k_eval_tiles<..., SEARCH = true>)
+struct SearchFuse {
+  float* cur_mk = nullptr;        // [chains] makespan of each chain's current candidate
+  uint8_t* cur_o = nullptr;       // writable views of the rows the EvalCall reads
+  uint8_t* cur_p = nullptr;
+  const uint8_t* vopt = nullptr;  // [J][8] proposable opt bytes
+  const int* nvalid = nullptr;    // [J]
+  uint64_t seed = 0, chain_base = 0;
+  int round = 0;
+  int nodes = 1;
+  float temperature = 0.f;
+};
+
 int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp);
 cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used);
+bool search_round_fits(const Device& dev, int J, int SG, int nodes);
+cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st);
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st);
 cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st);
 

@@ -188,8 +188,9 @@ class Engine:
     # ------------------------------------------------------------------ search
     def search_init(self, chains: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
                     reduced: bool = False, t_start: float = 0.02, t_end: float = 1e-4, total_rounds: int = 200,
-                    warm: Optional[Tuple[np.ndarray, np.ndarray]] = None):
-        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base, flags=_flags(integer_starts, reduced),
+                    warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, _no_fused: bool = False):
+        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base,
+                         flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
                          t_start=t_start, t_end=t_end, total_rounds=total_rounds)
         wo = wp = None
         keep = None
@@ -202,6 +203,9 @@ class Engine:
         del keep
         self._search_chains = chains
         self._search_base = chain_base
+
+    def search_is_fused(self) -> bool:
+        return bool(self._lib.sb_search_is_fused(self._h))
 
     def search_round(self, rounds: int = 1):
         check(self._lib.sb_search_round(self._h, rounds))

@@ -76,8 +76,13 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
                patience: Optional[int] = None, t_start: float = 5e-4, t_end: float = 1e-6,
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
                target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 4,
-               record_history: bool = False, heuristic_seeds: bool = True) -> SearchResult:
-    """Run the search on `engine` (table already set).  Returns the best candidate found by any rank."""
+               record_history: bool = False, heuristic_seeds: bool = True,
+               exchange_every: int = 4, _no_fused: bool = False) -> SearchResult:
+    """Run the search on `engine` (table already set).  Returns the best candidate found by any rank.
+
+    `rounds` device rounds are issued in groups of `exchange_every`; after each group the ranks
+    exchange their best key (one MIN all-reduce) and the stopping rules are evaluated, so the host
+    synchronises once per group rather than once per round."""
     dist = _dist() if use_dist else None
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
@@ -85,7 +90,8 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     pdt = np.uint8 if J <= 256 else np.uint16
     t0 = time.perf_counter()
     engine.search_init(chains, seed=seed, chain_base=rank * chains, integer_starts=integer_starts,
-                       reduced=reduced, t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1), warm=warm)
+                       reduced=reduced, t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1), warm=warm,
+                       **({"_no_fused": True} if _no_fused else {}))
     if heuristic_seeds:
         # every rank plants the longest-processing-time seeds in an eighth of its population each;
         # the rest stays random (diversity), tournament resampling then concentrates the population
@@ -115,15 +121,22 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     best_seen = key
     if record_history:
         history.append((time.perf_counter() - t0, chains * world, key_makespan(key)))
-    for r in range(rounds):
-        engine.search_round(1)
-        done_rounds += 1
+    exchange_every = max(1, int(exchange_every))
+    if resample_every:
+        exchange_every = min(exchange_every, int(resample_every))
+    while done_rounds < rounds:
+        step = min(exchange_every, rounds - done_rounds)
+        if resample_every:                      # keep resampling on its own cadence
+            step = min(step, resample_every - (done_rounds % resample_every))
+        engine.search_round(step)
+        done_rounds += step
+        r = done_rounds - 1
         key = exchange()
         if key < best_seen:
             best_seen = key
             stale = 0
         else:
-            stale += 1
+            stale += step
         if record_history:
             history.append((time.perf_counter() - t0, chains * world * (done_rounds + 1), key_makespan(key)))
         # stopping decisions must be identical on every rank: derive them from rank 0's clock

@@ -141,3 +141,29 @@ def test_multi_node_solve_matches_reference_milp(golden_n2):
         # warm start from the previous plan keeps working with nodes
         again = ss.solve(tasks, out, gurobi=False, timeout=60, chains=4096, rounds=20, nodes=2)
         assert again[5] <= mk * (1 + 1e-9)
+
+
+@pytest.mark.parametrize("J,S,nodes", [(64, 6, 1), (256, 8, 1), (100, 1, 2)])
+def test_fused_and_unfused_search_rounds(engine, J, S, nodes):
+    """The fused round (move + evaluate + accept in one kernel) and the propose / evaluate / accept
+    round are the same search: both improve on the seeded population, both return candidates whose
+    oracle makespan equals the reported one, and the chain state they leave behind is consistent
+    (re-evaluating the incumbent reproduces its key)."""
+    from saturn_b200.search import run_search
+    T, valid = R.synth_table(J, S, 8, seed=2, masked=(S > 1))
+    engine.set_table(T, nodes=nodes)
+    tab = R.canon_table(T, range(1, 9))
+    reduced = nodes > 1
+    if reduced:
+        tab = R.reduce_table(tab)[0][:, None, :]
+    res = {}
+    for fused in (True, False):
+        r = run_search(engine, chains=8192, rounds=40, seed=3, reduced=reduced, record_history=True, use_dist=False,
+                       _no_fused=not fused)
+        assert engine.search_is_fused() == fused
+        assert r.history[-1][2] < r.history[0][2]
+        mk = R.list_schedule(tab, r.opt, r.prio, True, np.float32, nodes=nodes)[0]
+        assert mk == r.makespan
+        assert sorted(r.prio.tolist()) == list(range(J))
+        res[fused] = r.makespan
+    assert abs(res[True] / res[False] - 1) < 0.02
