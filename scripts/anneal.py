@@ -34,8 +34,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        warm = torch.zeros(1, dtype=torch.int64, device="cuda")
+        dist.all_reduce(warm, op=dist.ReduceOp.MIN)          # communicator set-up is not part of the anneal
     J, S, G, seed = CONFIGS[args.config]
     T, valid = synth_table(J, S, G, seed=seed)
     eng = Engine(local)
