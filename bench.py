@@ -295,6 +295,34 @@ def main():
                "h2d_bytes_per_step": int(Be * stride * 2), "d2h_bytes_per_step": int(Be * 4),
                "candidates_per_gpu_per_step": Be, "api": "saturn_b200.engine.Engine.eval_host -> sb_eval_host"}
 
+    # ---- the reference-facing call itself: saturn.solver.solve(task_list) on host Task objects
+    solve_leg = None
+    if not args.no_e2e and args.config == "C4":
+        from saturn_b200 import Strategy, solve
+        from saturn_b200 import solver as sb_solver
+        import numpy as _np
+
+        class _Task:
+            def __init__(self, name, strategies):
+                self.name, self.strategies, self.selected_strategy = name, strategies, None
+
+            def select_strategy(self, st_):
+                self.selected_strategy = st_
+
+        tmin_h = _np.where(valid, T, _np.inf).min(axis=1)
+        tasks = [_Task("t%d" % j, {g + 1: Strategy("x", g + 1, {}, float(tmin_h[j, g])) for g in range(G)
+                                    if _np.isfinite(tmin_h[j, g])}) for j in range(J)]
+        solve(tasks, None, engine=eng, chains=1 << 17, rounds=8)                  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        plan = solve(tasks, None, engine=eng, chains=1 << 17, rounds=200)
+        dt = time.perf_counter() - t0
+        stt = dict(sb_solver.last_stats)
+        eng.set_table(T)                                                          # restore the bench table
+        solve_leg = {"value": stt["candidates"] / dt, "unit": UNIT, "wall_s": dt, "candidates": stt["candidates"],
+                     "makespan": plan[5], "h2d_bytes": int(J * 8 * 4), "d2h_bytes": int(J * (8 + 4 + 1 + 1 + 1)),
+                     "api": "saturn.solver.solve(task_list) -> (sta, tga, bss, bna, boa, makespan); per rank"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         alg = B * bytes_per_candidate(J)
@@ -303,8 +331,9 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": dram if args.config == "C4" else None, "eval_path": kernel_path, "kernel": "k_eval_tiles<1,%s,true>" % ("true" if ints else "false"),
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                "note": "the kernel is ALU-issue bound (one list-scheduling step = ~60 SASS instructions per "
-                        "candidate), not HBM bound; see DESIGN.md"}
+                "note": "instruction-issue bound, not HBM bound: one list-scheduling step is ~57 SASS "
+                        "instructions per candidate for 2 bytes of input (89 % of issue slots used); see "
+                        "DESIGN.md 5.1 and profiles/r01_summary.md"}
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle
@@ -321,7 +350,8 @@ def main():
                            "l2": "inputs (%.0f MB of encodings per GPU per step) exceed the 126 MB L2"
                                  % (B * 2 * opt.stride(0) / 1e6),
                            "exchange": "one all_reduce(MIN) of a uint64 per step" if world > 1 else "none (N=1)"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "solve_api": solve_leg, "gpu_launches": args.steps, "roofline": roof,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

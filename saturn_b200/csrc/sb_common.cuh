@@ -98,6 +98,13 @@ __device__ __forceinline__ void pinf_fma(float& dst, int bit) {
   asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p add.f32 %0, %0, 0f7F800000;\n\t}" : "+f"(dst) : "r"(bit));
 }
 
+// bit ? a : b with the predicate formed inside the asm (FSEL on the ALU pipe)
+__device__ __forceinline__ float psel(float a, float b, int bit) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"(bit));
+  return r;
+}
+
 #ifndef SB_STAGE4_FMA
 #define SB_STAGE4_FMA 2
 #endif
@@ -123,14 +130,14 @@ __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int 
   pmov_fma(x0, f[4], b2i, one); pmov_fma(x1, f[5], b2i, one); pmov_fma(x2, f[6], b2i, one); pmov_fma(x3, f[7], b2i, one);
   pinf_fma(x4, b2i); pinf_fma(x5, b2i); pinf_fma(x6, b2i); pinf_fma(x7, b2i);
 #else
-  // stage "shift by 4" (ALU pipe: FSEL / SEL)
-  const bool b2 = (km1 & 4) != 0;
-  float x0 = b2 ? f[4] : f[0], x1 = b2 ? f[5] : f[1], x2 = b2 ? f[6] : f[2], x3 = b2 ? f[7] : f[3];
+  // stage "shift by 4", lower half on the ALU pipe (FSEL).  The predicate is formed from the bit
+  // inside the asm so that ptxas derives all three stage predicates with one R2P.
+  const int b2i = km1 & 4;
+  float x0 = psel(f[4], f[0], b2i), x1 = psel(f[5], f[1], b2i), x2 = psel(f[6], f[2], b2i), x3 = psel(f[7], f[3], b2i);
 #if SB_STAGE4_FMA == 0
-  float x4 = b2 ? INF : f[4], x5 = b2 ? INF : f[5], x6 = b2 ? INF : f[6], x7 = b2 ? INF : f[7];
+  float x4 = psel(INF, f[4], b2i), x5 = psel(INF, f[5], b2i), x6 = psel(INF, f[6], b2i), x7 = psel(INF, f[7], b2i);
 #else
   // upper half: copy on the FMA pipe (FADD of a run-time -0.0) + predicated FADD of +inf
-  const int b2i = km1 & 4;
   const float nz = __int_as_float(one << 31);
   float x4 = copy_fadd(f[4], nz), x5 = copy_fadd(f[5], nz), x6 = copy_fadd(f[6], nz), x7 = copy_fadd(f[7], nz);
   pinf_fma(x4, b2i); pinf_fma(x5, b2i); pinf_fma(x6, b2i); pinf_fma(x7, b2i);

@@ -102,8 +102,10 @@ struct LaneState {
 
 template <int PB>
 __device__ __forceinline__ int prio_at(const uint32_t* w, int t) {
-  if (PB == 1) return (w[t >> 2] >> ((t & 3) * 8)) & 0xff;
-  return (w[t >> 1] >> ((t & 1) * 16)) & 0xffff;
+  // one PRMT per position: pick byte(s) t of the word, zero the rest (selector nibble 4 = byte 0 of
+  // the second operand, which is 0)
+  if (PB == 1) return static_cast<int>(__byte_perm(w[t >> 2], 0u, 0x4440u + (t & 3)));
+  return static_cast<int>(__byte_perm(w[t >> 1], 0u, (t & 1) ? 0x4432u : 0x4410u));
 }
 
 __device__ __forceinline__ void fold_best(unsigned long long* best_key, bool active, float mk, uint32_t id, int lane) {
