@@ -193,12 +193,13 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   cudaError_t pe = cudaPointerGetAttributes(&attr, T);
   const bool on_device = (pe == cudaSuccess) && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
   if (pe != cudaSuccess) cudaGetLastError();
+  cudaError_t e = cudaSuccess;
   if (!on_device) {
-    CK(cudaMalloc(&tmp, nT * sizeof(float)));
-    CK(cudaMemcpyAsync(tmp, T, nT * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    e = cudaMalloc(&tmp, nT * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, T, nT * sizeof(float), cudaMemcpyHostToDevice, h->stream);
     Tdev = tmp;
   }
-  cudaError_t e = build_table_launch(Tdev, J, S, G, packed, h->tab, h->tmin, h->args, h->stream);
+  if (e == cudaSuccess) e = build_table_launch(Tdev, J, S, G, packed, h->tab, h->tmin, h->args, h->stream);
   if (e == cudaSuccess) e = build_valid_launch(h->tmin, h->args, J, 0, h->sentinel, h->vopt[0], h->nvalid[0], h->stream);
   if (e == cudaSuccess) e = build_valid_launch(h->tmin, h->args, J, 1, h->sentinel, h->vopt[1], h->nvalid[1], h->stream);
   h->h_tmin.assign(static_cast<size_t>(J) * kSlots, 0.f);
@@ -208,7 +209,7 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h->h_args.data(), h->args, h->h_args.size(), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (tmp) cudaFree(tmp);
+  if (tmp) cudaFree(tmp);  // released on every path, including errors
   if (e != cudaSuccess) {
     free_table(h);
     return fail(SB_ERR_CUDA, "building the table failed: %s", cudaGetErrorString(e));

@@ -223,7 +223,7 @@ __device__ __forceinline__ void write_back(const Move& m, const uint8_t* orow, c
 }
 
 template <int PB, bool INT, bool STREAM, bool MULTI, bool SEARCH = false>
-__global__ void __launch_bounds__(STREAM ? 512 : 256, 1) k_eval_tiles(const TileArgs a) {
+__global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const TileArgs a) {
   static_assert(!(SEARCH && STREAM), "the fused search round mutates shared-memory rows");
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
@@ -541,7 +541,7 @@ int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes,
   const size_t tab_bytes = (static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15);
   const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + (stream ? 0 : tp->row_p)) +
                           (nodes > 1 ? static_cast<size_t>(nodes) * 1024u : 0u);
-  int nw = stream ? 16 : 8;
+  int nw = stream ? 16 : 12;  // block size limits: 512 / 384 threads (128 registers per thread)
   while (nw > 0 && tab_bytes + 16 * ((1 + nw + 1) / 2) + nw * per_warp > dev.smem_optin) --nw;
   tp->warps = nw;
   tp->smem = tab_bytes + (((1 + nw) * 8 + 15) & ~15) + nw * per_warp;

@@ -143,7 +143,7 @@ def test_multi_node_solve_matches_reference_milp(golden_n2):
         assert again[5] <= mk * (1 + 1e-9)
 
 
-@pytest.mark.parametrize("J,S,nodes", [(64, 6, 1), (256, 8, 1), (100, 1, 2)])
+@pytest.mark.parametrize("J,S,nodes", [(64, 6, 1), (256, 8, 1), (100, 1, 2), (400, 1, 1)])
 def test_fused_and_unfused_search_rounds(engine, J, S, nodes):
     """The fused round (move + evaluate + accept in one kernel) and the propose / evaluate / accept
     round are the same search: both improve on the seeded population, both return candidates whose
