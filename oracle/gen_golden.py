@@ -153,7 +153,47 @@ def main_nodes(nodes):
     print("wrote", dst)
 
 
+def main_forecast():
+    """Fixtures for the interval loop: the reference's own forecast() (saturn/executor/executor.py:132-178)
+    on duck-typed tasks; records its return values and the mutations it applies to the tasks."""
+    milp, tight, Strategy, pulp = _load_reference()
+    from saturn.executor import forecast           # the reference, unmodified (ray shim on sys.path)
+    assert forecast.__code__.co_filename.startswith(REF)
+    rnd = random.Random(5)
+    out = {"generator": "oracle/gen_golden.py --forecast", "reference_commit": "b65e3d2", "cases": []}
+    for case in range(6):
+        J = rnd.randint(2, 7)
+        interval = rnd.choice([100, 500, 1000])
+        tasks, spec = [], []
+        for t in range(J):
+            base = rnd.uniform(50, 3000)
+            opts = rnd.sample([1, 2, 4, 8], rnd.randint(1, 3))
+            strategies = {g: Strategy("e", g, {}, base / g ** 0.8) for g in opts}
+            task = DuckTask("t%d" % t, strategies)
+            task.total_batches = rnd.randint(1, 400)
+            task.select_strategy(strategies[rnd.choice(opts)])
+            tasks.append(task)
+            spec.append({"strategies": [[g, s.runtime] for g, s in strategies.items()],
+                         "total_batches": task.total_batches,
+                         "selected": task.selected_strategy.gpu_apportionment})
+        starts = [float(rnd.choice([0, 0, rnd.randint(0, 2 * interval)])) for _ in range(J)]
+        rel, btr, done = forecast(tasks, interval, starts)
+        idx = {t: i for i, t in enumerate(tasks)}
+        out["cases"].append({
+            "interval": interval, "starts": starts, "tasks": spec,
+            "relevant": [idx[t] for t in rel], "batches_to_run": [float(b) for b in btr],
+            "completed": sorted(idx[t] for t in done),
+            "after": [{"total_batches": t.total_batches,
+                       "runtimes": [[g, s.runtime] for g, s in t.strategies.items()]} for t in tasks]})
+    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "forecast_cases.json")
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", dst, len(out["cases"]), "cases")
+
+
 def main():
+    if "--forecast" in sys.argv:
+        return main_forecast()
     if "--nodes" in sys.argv:
         return main_nodes(int(sys.argv[sys.argv.index("--nodes") + 1]))
     milp, tight, Strategy, pulp = _load_reference()

@@ -199,3 +199,27 @@ def test_multi_node_plan_arrays_and_decoder(golden_n2):
         idx = {t: i for i, t in enumerate(tasks)}
         assert [int(npt[t]) for t in tasks] == d["node_per_task"] and [float(x) for x in st] == d["start"]
         assert [sorted(idx[x] for x in tdd[t]) for t in tasks] == d["deps"]
+
+
+def test_forecast_matches_reference_forecast():
+    """forecast() against the reference's own forecast (executor.py:132-178) run unmodified when the
+    fixtures were generated: same tasks launched, same batch counts, same completed set, and the same
+    in-place mutations of every strategy runtime and of total_batches."""
+    import json
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "forecast_cases.json")))
+    assert len(d["cases"]) >= 5
+    for case in d["cases"]:
+        tasks = []
+        for t, spec in enumerate(case["tasks"]):
+            task = DuckTask("t%d" % t, {int(g): Strategy("e", int(g), {}, float(rt)) for g, rt in spec["strategies"]},
+                            total_batches=spec["total_batches"])
+            task.select_strategy(task.strategies[spec["selected"]])
+            tasks.append(task)
+        rel, btr, done = forecast(tasks, case["interval"], case["starts"])
+        idx = {t: i for i, t in enumerate(tasks)}
+        assert [idx[t] for t in rel] == case["relevant"]
+        assert [float(b) for b in btr] == case["batches_to_run"]
+        assert sorted(idx[t] for t in done) == case["completed"]
+        for task, after in zip(tasks, case["after"]):
+            assert task.total_batches == after["total_batches"]
+            assert [[g, s.runtime] for g, s in task.strategies.items()] == after["runtimes"]
