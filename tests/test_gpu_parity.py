@@ -276,3 +276,61 @@ def test_multi_node_parity(engine, J, nodes, B, ints):
     bad.copy_(opt)
     bad[5, 2] = (nodes << 3) | 1                                  # a node that does not exist
     assert engine.validate(bad, prio, reduced=True) == 1
+
+
+def test_fuzz_small_and_odd_shapes(engine):
+    """Seeded sweep over small / odd shapes (J from 1, ragged GPU-count sets, 1-3 nodes, both start
+    modes, aligned and unaligned rows): every kernel path must equal the Python oracle exactly."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        J = int(rng.integers(1, 41))
+        nodes = int(rng.choice([1, 1, 2, 3]))
+        S = 1 if nodes > 1 else int(rng.integers(1, 5))
+        G = int(rng.integers(1, 9))
+        gcount = sorted(rng.choice(np.arange(1, 9), size=G, replace=False).tolist())
+        ints = bool(rng.integers(0, 2))
+        B = int(rng.integers(1, 90))
+        T = rng.uniform(1.0, 900.0, size=(J, S, G)).astype(np.float32)
+        if trial % 3 == 0:
+            T = np.ceil(T)                                  # integer runtimes: lots of exact ties
+        engine.set_table(T, gcount, nodes=nodes)
+        tab = R.canon_table(T, gcount)
+        valid = np.ones((J, S, G), dtype=bool)
+        opt, prio = random_candidates(engine, B, valid, seed=trial, nodes=nodes)
+        red = nodes > 1
+        o_np, p_np = opt.cpu().numpy(), prio.cpu().numpy()
+        ref = np.array([R.list_schedule(tab, o_np[b], p_np[b], ints, np.float32, nodes=nodes)[0] for b in range(B)],
+                       dtype=np.float32)
+        for kw in ({}, {"_no_stream": True}, {"_force_generic": True}):
+            got = engine.eval(opt, prio, integer_starts=ints, reduced=red, **kw).cpu().numpy()
+            assert np.array_equal(got, ref), (trial, J, S, gcount, nodes, ints, kw)
+        got = engine.eval(opt.contiguous(), prio.contiguous(), integer_starts=ints, reduced=red).cpu().numpy()
+        assert np.array_equal(got, ref), (trial, "unaligned")
+        mk, start, mask = engine.eval_full(opt, prio, integer_starts=ints, reduced=red)
+        b = int(rng.integers(0, B))
+        m1, s1, k1, _ = R.list_schedule(tab, o_np[b], p_np[b], ints, np.float32, nodes=nodes)
+        assert float(mk[b]) == m1 and mask[b].cpu().numpy().astype(np.uint32).tolist() == k1
+        assert [float(x) for x in start[b].cpu().numpy()] == [float(x) for x in s1]
+
+
+def test_large_batch_64bit_indexing(engine):
+    """9.4 M candidates of J = 256: each encoding array is 2.4 GB, so row offsets exceed 2^31 bytes."""
+    J, S, G = 256, 8, 8
+    B = 148 * 16 * 32 * 124                                  # 9,396,224
+    T, valid = R.synth_table(J, S, G, seed=0)
+    engine.set_table(T)
+    opt, prio = random_candidates(engine, B, valid, seed=77)
+    assert opt.stride(0) * (B - 1) > 2 ** 31
+    key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=engine.device)
+    out = engine.eval(opt, prio, best_key=key)
+    torch.cuda.synchronize()
+    tab = R.canon_table(T, range(1, 9))
+    for lo in (0, B // 2 + 12345, B - 4000):
+        sl = slice(lo, lo + 4000)
+        ref = c_oracle.evaluate(tab, opt[sl].cpu().numpy(), prio[sl].cpu().numpy(), True, np.float32, threads=8)
+        assert np.array_equal(out[sl].cpu().numpy(), ref)
+    k = int(key.item())
+    assert np.array([(k >> 32)], dtype=np.uint32).view(np.float32)[0] == float(out.min())
+    assert int(out.argmin()) == (k & 0xffffffff)
+    del opt, prio, out
+    torch.cuda.empty_cache()
