@@ -80,6 +80,25 @@ struct LaneState {
       for (int n = 0; n < 2 * nodes; ++n) ns[n * 32] = z;
     }
   }
+  // the two look-ups of a step (opt byte, then runtime) do not depend on the slot state, so callers
+  // that read from global memory resolve a batch of positions first (memory-level parallelism)
+  __device__ __forceinline__ int lookup_opt(int j) const { return orow[j]; }
+  __device__ __forceinline__ float lookup_rt(int j, int o) const {
+    return MULTI ? tab[j * 8 + (o & 7)] : tab[j * SG + o];
+  }
+  __device__ __forceinline__ void step_resolved(int o, float rt) {
+    if (!MULTI) {
+      ls_step<INT>(f, mk, rt, o & 7, one);
+    } else {
+      float4* slot = ns + (2 * (o >> 3)) * 32;
+      const float4 lo = slot[0], hi = slot[32];
+      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
+      f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+      ls_step<INT, true>(f, mk, rt, o & 7, one);
+      slot[0] = make_float4(f[0], f[1], f[2], f[3]);
+      slot[32] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
   __device__ __forceinline__ void step(int j) {
     const int o = orow[j];
     if (!MULTI) {
@@ -416,7 +435,23 @@ __global__ void __launch_bounds__(128) k_eval_generic(const GenericArgs a) {
       st.orow = a.opt + b * a.stride_o;
       const uint8_t* prow = a.prio + b * a.stride_p;
       st.reset(a.nodes);
-      for (int i = 0; i < a.J; ++i) st.step(PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i]);
+      // batches of 16 positions: 16 independent opt loads, then 16 independent table loads, then the
+      // 16 dependent scheduling steps — the global-memory latency is paid once per batch
+      constexpr int BATCH = 16;
+      int i = 0;
+      for (; i + BATCH <= a.J; i += BATCH) {
+        int js[BATCH], os[BATCH];
+        float rts[BATCH];
+#pragma unroll
+        for (int t = 0; t < BATCH; ++t) js[t] = PB == 1 ? prow[i + t] : reinterpret_cast<const uint16_t*>(prow)[i + t];
+#pragma unroll
+        for (int t = 0; t < BATCH; ++t) os[t] = st.lookup_opt(js[t]);
+#pragma unroll
+        for (int t = 0; t < BATCH; ++t) rts[t] = st.lookup_rt(js[t], os[t]);
+#pragma unroll
+        for (int t = 0; t < BATCH; ++t) st.step_resolved(os[t], rts[t]);
+      }
+      for (; i < a.J; ++i) st.step(PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i]);
       mk = st.result();
       a.out[b] = mk;
     }
