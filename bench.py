@@ -225,14 +225,12 @@ def main():
     opt, prio = random_candidates(eng, B, valid, seed=1 + rank)
     out = torch.empty(B, dtype=torch.float32, device=dev)
     key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=dev)
-    gkey = torch.empty_like(key)
     id_base = (rank * B) & 0xffffffff
 
     def step():
         eng.eval(opt, prio, integer_starts=ints, out=out, best_key=key, id_base=id_base)
         if world > 1:
-            gkey.copy_(key)
-            dist.all_reduce(gkey, op=dist.ReduceOp.MIN)
+            dist.all_reduce(key, op=dist.ReduceOp.MIN)      # in place: the running best becomes global
 
     def barrier():
         if world > 1:
@@ -259,8 +257,7 @@ def main():
         eng.eval(opt, prio, integer_starts=ints, out=out, best_key=key, id_base=id_base)
         k_ev[i][1].record()
         if world > 1:
-            gkey.copy_(key)
-            dist.all_reduce(gkey, op=dist.ReduceOp.MIN)
+            dist.all_reduce(key, op=dist.ReduceOp.MIN)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -167,3 +167,19 @@ def test_fused_and_unfused_search_rounds(engine, J, S, nodes):
         assert sorted(r.prio.tolist()) == list(range(J))
         res[fused] = r.makespan
     assert abs(res[True] / res[False] - 1) < 0.02
+
+
+@pytest.mark.parametrize("J,chains", [(1, 1), (2, 5), (3, 33), (7, 64)])
+def test_tiny_problems_and_populations(J, chains):
+    """Degenerate sizes: one task, populations smaller than a warp — the plan is still feasible and,
+    being enumerable, optimal."""
+    from saturn_b200 import solve
+    rng = np.random.default_rng(J)
+    tuples = [[(g, float(rng.uniform(10, 500)) / g ** 0.7) for g in (1, 4, 8)] for _ in range(J)]
+    tasks = tasks_from_tuples(tuples)
+    out = solve(tasks, None, chains=chains, rounds=40)
+    mk = _check_plan(tasks, out)
+    if J <= 3:
+        tab, om = R.table_from_tuples(tuples)
+        assert mk == pytest.approx(R.brute_force(tab, om, True)[0], rel=1e-9)
+    assert solve([], None) [5] == 0.0
