@@ -107,6 +107,7 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
             unsigned flags, float* makespan_out, uint64_t* best_key, uint32_t id_base);
 
 /* which kernel the last sb_eval / sb_eval_host on this handle used:
+ * 4 = as 3 but with the runtime table read from global memory (it does not fit in shared memory),
  * 3 = tile kernel, opt rows by TMA bulk copy + prio rows streamed with 256-bit loads (rows 32-byte
  *     aligned: the fast path), 2 = tile kernel with TMA bulk copies of both rows (16-byte aligned),
  * 1 = tile kernel with plain row loads (unaligned rows),

@@ -241,13 +241,15 @@ __device__ __forceinline__ void write_back(const Move& m, const uint8_t* orow, c
   }
 }
 
-template <int PB, bool INT, bool STREAM, bool MULTI, bool SEARCH = false>
+// TABG: the runtime table stays in global memory (read through L1/L2) — for tables larger than the
+// shared memory left beside the opt tiles (e.g. J = 1024 with 8 strategies: 256 KB).
+template <int PB, bool INT, bool STREAM, bool MULTI, bool SEARCH = false, bool TABG = false>
 __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const TileArgs a) {
   static_assert(!(SEARCH && STREAM), "the fused search round mutates shared-memory rows");
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tab_bytes = static_cast<uint32_t>(a.J) * a.SG * 4u;
+  const uint32_t tab_bytes = TABG ? 0u : static_cast<uint32_t>(a.J) * a.SG * 4u;
   float* tab_s = reinterpret_cast<float*>(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((tab_bytes + 15u) & ~15u));
   uint8_t* tiles = reinterpret_cast<uint8_t*>(bars) + (((1 + nw) * 8 + 15) & ~15);
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     mbar_fence_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (!TABG && threadIdx.x == 0) {
     // stage the runtime table: TMA bulk copies of <= 32 KB each, one mbarrier phase
     mbar_arrive_expect_tx(bar_tab, tab_bytes);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab);
@@ -277,14 +279,15 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
   }
 
   LaneState<INT, MULTI> st;
-  st.tab = tab_s;
+  if (TABG) st.tab = a.tab;
+  else st.tab = tab_s;
   st.SG = a.SG;
   st.one = a.one;
   st.orow = tile_o + lane * a.row_o;
   st.ns = node_s + lane;
 
   uint32_t phase = 0;
-  bool tab_ready = false;
+  bool tab_ready = TABG;
   for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
        tile += static_cast<long long>(gridDim.x) * nw) {
     const long long b0 = tile * 32;
@@ -568,12 +571,12 @@ static int round_row(int bytes) {
   return r16 * 16;
 }
 
-int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp) {
+int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp, bool tab_global) {
   tp->row_o = round_row(J);
   tp->row_p = round_row(J * pb);
   tp->copy_o = (J + 15) & ~15;
   tp->copy_p = (J * pb + 15) & ~15;
-  const size_t tab_bytes = (static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15);
+  const size_t tab_bytes = tab_global ? 0 : ((static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15));
   const size_t per_warp = 32u * static_cast<size_t>(tp->row_o + (stream ? 0 : tp->row_p)) +
                           (nodes > 1 ? static_cast<size_t>(nodes) * 1024u : 0u);
   int nw = stream ? 16 : 12;  // block size limits: 512 / 384 threads (128 registers per thread)
@@ -583,9 +586,9 @@ int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes,
   return nw;
 }
 
-template <int PB, bool INT, bool STREAM, bool MULTI>
+template <int PB, bool INT, bool STREAM, bool MULTI, bool TABG = false>
 static cudaError_t launch_tiles(const Device& dev, const TileArgs& a, const TilePlan& tp, cudaStream_t st) {
-  auto kern = k_eval_tiles<PB, INT, STREAM, MULTI>;
+  auto kern = k_eval_tiles<PB, INT, STREAM, MULTI, false, TABG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
   if (e != cudaSuccess) return e;
   long long ctas = (a.ntiles + tp.warps - 1) / tp.warps;
@@ -637,11 +640,16 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
                          !(c.flags & 0x40000000u);
   TilePlan tp;
   int nw = 0;
-  bool stream = false;
+  bool stream = false, tabg = false;
   if (!c.force_generic) {
     if (stream_ok) {
       nw = plan_tiles(dev, c.J, c.SG, pb, true, c.nodes, &tp);
       stream = nw >= 2 && c.stride_o >= tp.copy_o && c.stride_p >= ((c.J * pb + 31) & ~31);
+      if (!stream && !multi) {
+        // the table itself does not fit beside the tiles: keep it in global memory
+        nw = plan_tiles(dev, c.J, c.SG, pb, true, c.nodes, &tp, true);
+        stream = tabg = nw >= 2 && c.stride_o >= tp.copy_o && c.stride_p >= ((c.J * pb + 31) & ~31);
+      }
     }
     if (!stream) nw = plan_tiles(dev, c.J, c.SG, pb, false, c.nodes, &tp);
   }
@@ -655,7 +663,11 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
     a.out = c.out; a.best_key = c.best_key; a.id_base = c.id_base;
     a.ntiles = (c.B + 31) / 32;
     a.one = 1;
-    if (path_used) *path_used = stream ? 3 : (a.use_bulk ? 2 : 1);
+    if (path_used) *path_used = tabg ? 4 : (stream ? 3 : (a.use_bulk ? 2 : 1));
+    if (tabg) {
+      if (pb == 1) return ints ? launch_tiles<1, true, true, false, true>(dev, a, tp, st) : launch_tiles<1, false, true, false, true>(dev, a, tp, st);
+      return ints ? launch_tiles<2, true, true, false, true>(dev, a, tp, st) : launch_tiles<2, false, true, false, true>(dev, a, tp, st);
+    }
     if (pb == 1) return ints ? dispatch_tiles<1, true>(dev, a, tp, stream, multi, st) : dispatch_tiles<1, false>(dev, a, tp, stream, multi, st);
     return ints ? dispatch_tiles<2, true>(dev, a, tp, stream, multi, st) : dispatch_tiles<2, false>(dev, a, tp, stream, multi, st);
   }

@@ -47,7 +47,7 @@ struct SearchFuse {
   float temperature = 0.f;
 };
 
-int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp);
+int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp, bool tab_global = false);
 cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used);
 bool search_round_fits(const Device& dev, int J, int SG, int nodes);
 cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st);

@@ -334,3 +334,18 @@ def test_large_batch_64bit_indexing(engine):
     assert int(out.argmin()) == (k & 0xffffffff)
     del opt, prio, out
     torch.cuda.empty_cache()
+
+
+def test_large_table_in_global_memory(engine):
+    """J = 1024 with the full 8-strategy table (256 KB) does not fit in shared memory: the tile kernel
+    keeps the table in global memory (path 4); results still equal the oracle and the generic kernel."""
+    J, S, G, B = 1024, 8, 8, 3000
+    T, valid = R.synth_table(J, S, G, seed=5)
+    engine.set_table(T)
+    tab = R.canon_table(T, range(1, 9))
+    opt, prio = random_candidates(engine, B, valid, seed=6)
+    a = engine.eval(opt, prio)
+    assert engine.last_eval_path() == 4
+    ref = c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy().astype(np.uint16), True, np.float32, threads=8)
+    assert np.array_equal(a.cpu().numpy(), ref)
+    assert torch.equal(a, engine.eval(opt, prio, _force_generic=True))
