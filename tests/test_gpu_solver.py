@@ -183,3 +183,26 @@ def test_tiny_problems_and_populations(J, chains):
         tab, om = R.table_from_tuples(tuples)
         assert mk == pytest.approx(R.brute_force(tab, om, True)[0], rel=1e-9)
     assert solve([], None) [5] == 0.0
+
+
+def test_solve_reaches_the_exhaustive_optimum_on_random_small_instances():
+    """24 random instances (2-4 tasks, ragged option lists, 1 or 2 nodes): the plan returned by
+    solve() is feasible under the reference's constraints and its makespan equals the exhaustive
+    list-scheduling optimum — which is the reference MILP's optimum on every fixture."""
+    from saturn_b200 import solve
+    rng = np.random.default_rng(99)
+    for trial in range(24):
+        J = int(rng.integers(2, 5))
+        nodes = int(rng.choice([1, 2]))
+        tuples = []
+        for _ in range(J):
+            ks = sorted(rng.choice([1, 2, 3, 4, 6, 8], size=int(rng.integers(1, 4)), replace=False).tolist())
+            base = float(rng.uniform(20, 900))
+            tuples.append([(int(k), base * float(rng.uniform(1, 1.3)) / k ** float(rng.uniform(0.4, 1.0))) for k in ks])
+        tasks = tasks_from_tuples(tuples)
+        out = solve(tasks, None, chains=4096, rounds=48, nodes=nodes, seed=trial)
+        sta, tga, bss, bna, boa, mk = out
+        assert R.milp_constraints_hold(tuples, sta, tga, bss, bna, boa, mk) == [], trial
+        tab, om = R.table_from_tuples(tuples)
+        best = R.brute_force(tab, om, True, nodes=nodes)[0]
+        assert mk == pytest.approx(best, rel=1e-9), (trial, J, nodes, tuples)
