@@ -72,6 +72,8 @@ def build_table(task_list):
             if not isinstance(g_count, (int, np.integer)) or g_count < 1 or g_count > NSLOT:
                 continue
             rt = strat.runtime
+            if rt is not None and -1e-6 <= rt < 0:
+                rt = 0.0        # forecast's in-place decrements (executor.py:166-168) can undershoot by an ulp
             if rt is None or not math.isfinite(rt) or rt < 0:
                 continue
             v = _f32_ceil(float(rt))
