@@ -75,14 +75,23 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // A job with k = km1 + 1 GPUs starts at s = f[km1] (the k-th smallest), and the k smallest
 // entries are replaced by v = s + hold.  With sh[i] = f[i + k] (+inf past the end) the new sorted
 // state is  f'[i] = max(f[i], min(v, sh[i]))  — every surviving element below v moves down k
-// places, the k copies of v follow, larger elements stay.  sh is produced by a 3-stage barrel
-// shifter on the bits of km1, no dynamic register indexing and no divergence.
+// places, the k copies of v follow, larger elements stay.  sh (and s, as element -1 of the same
+// window) is produced by a 3-stage barrel shifter on the bits of km1: no dynamic register
+// indexing, no divergence.
 //
-// Pipe balance (ncu, profiles/r01_*): with all 24 barrel selects as FSEL the kernel saturates the
-// ALU pipe (96 % busy) while the FMA pipe idles at 4 %.  Stages 2 and 1 are therefore written as
-// in-place predicated moves expressed as `@p mad.lo dst, src, one, 0` with `one` a run-time 1
-// (a kernel argument, so ptxas cannot fold it back into SEL): they issue as predicated IMAD on
-// the FMA pipe.  Moving in ascending index order reads only not-yet-overwritten sources.
+// Instruction mix, shaped by the ncu captures in profiles/r01_summary.md — the kernel is bound by
+// instruction issue, and before that by the ALU pipe, so work is spread over the pipes at the
+// lowest instruction count found (54 per step):
+//   stage "by 4", lower half : 4 FSEL (ALU); predicates come from the bit inside the asm so that
+//                              ptxas derives all three stage predicates with ONE R2P of the opt byte
+//   stage "by 4", upper half : x = f + m with m = bit ? +inf : -0.0  (1 FSEL + 4 FADD, FMA pipe;
+//                              f + -0.0 == f exactly, f + inf == inf) — doubles as the copy that
+//                              keeps f intact for the final max
+//   stages "by 2", "by 1"    : in-place predicated moves written as `@p mad.lo dst, src, one, 0`
+//                              with `one` a run-time 1, so ptxas cannot fold them into SEL: they
+//                              issue as predicated IMAD on the FMA pipe; +inf padding as predicated
+//                              `add dst, dst, +inf`.  Ascending order reads only unmodified sources.
+//   merge                    : 7 FMNMX (min) + 8 FMNMX (max) on the ALU pipe.
 __device__ __forceinline__ void pmov_fma(float& dst, float src, int bit, int one) {
   int d = __float_as_int(dst);
   asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mad.lo.s32 %0, %1, %3, 0;\n\t}"
@@ -90,27 +99,15 @@ __device__ __forceinline__ void pmov_fma(float& dst, float src, int bit, int one
       : "r"(__float_as_int(src)), "r"(bit), "r"(one));
   dst = __int_as_float(d);
 }
-
-// dst = +inf under the predicate, as `@p add.f32 dst, dst, +inf` (x + inf = inf for every x >= 0):
-// it depends on dst, so ptxas cannot hoist it into a SEL of a loop-invariant; it issues as a
-// predicated FADD on the FMA pipe.
+// dst = +inf under the predicate, as `@p add.f32 dst, dst, +inf`: it depends on dst, so ptxas cannot
+// hoist it into a SEL of a loop-invariant.
 __device__ __forceinline__ void pinf_fma(float& dst, int bit) {
   asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p add.f32 %0, %0, 0f7F800000;\n\t}" : "+f"(dst) : "r"(bit));
 }
-
-// bit ? a : b with the predicate formed inside the asm (FSEL on the ALU pipe)
+// bit ? a : b with the predicate formed inside the asm (FSEL)
 __device__ __forceinline__ float psel(float a, float b, int bit) {
   float r;
   asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"(bit));
-  return r;
-}
-
-#ifndef SB_STAGE4_FMA
-#define SB_STAGE4_FMA 2
-#endif
-__device__ __forceinline__ float copy_fadd(float x, float negzero) {
-  float r;
-  asm("add.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(negzero));
   return r;
 }
 
@@ -119,31 +116,12 @@ __device__ __forceinline__ float copy_fadd(float x, float negzero) {
 template <bool kIntegerStarts, bool kTrackMk = kIntegerStarts>
 __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1, int one) {
   const float INF = inf_f();
-  const int b1 = km1 & 2, b0 = km1 & 1;
-#if SB_STAGE4_FMA == 1
-  // stage "shift by 4" on the FMA pipe as well: copy (an FADD of -0.0 the compiler cannot fold:
-  // the addend is `one`-derived) + in-place predicated IMAD
-  const int b2i = km1 & 4;
-  const float nz = __int_as_float(one << 31);  // -0.0f at run time
-  float x0 = copy_fadd(f[0], nz), x1 = copy_fadd(f[1], nz), x2 = copy_fadd(f[2], nz), x3 = copy_fadd(f[3], nz);
-  float x4 = copy_fadd(f[4], nz), x5 = copy_fadd(f[5], nz), x6 = copy_fadd(f[6], nz), x7 = copy_fadd(f[7], nz);
-  pmov_fma(x0, f[4], b2i, one); pmov_fma(x1, f[5], b2i, one); pmov_fma(x2, f[6], b2i, one); pmov_fma(x3, f[7], b2i, one);
-  pinf_fma(x4, b2i); pinf_fma(x5, b2i); pinf_fma(x6, b2i); pinf_fma(x7, b2i);
-#else
-  // stage "shift by 4", lower half on the ALU pipe (FSEL).  The predicate is formed from the bit
-  // inside the asm so that ptxas derives all three stage predicates with one R2P.
-  const int b2i = km1 & 4;
-  float x0 = psel(f[4], f[0], b2i), x1 = psel(f[5], f[1], b2i), x2 = psel(f[6], f[2], b2i), x3 = psel(f[7], f[3], b2i);
-#if SB_STAGE4_FMA == 0
-  float x4 = psel(INF, f[4], b2i), x5 = psel(INF, f[5], b2i), x6 = psel(INF, f[6], b2i), x7 = psel(INF, f[7], b2i);
-#else
-  // upper half: copy on the FMA pipe (FADD of a run-time -0.0) + predicated FADD of +inf
-  const float nz = __int_as_float(one << 31);
-  float x4 = copy_fadd(f[4], nz), x5 = copy_fadd(f[5], nz), x6 = copy_fadd(f[6], nz), x7 = copy_fadd(f[7], nz);
-  pinf_fma(x4, b2i); pinf_fma(x5, b2i); pinf_fma(x6, b2i); pinf_fma(x7, b2i);
-#endif
-#endif
-  // stage "shift by 2" (FMA pipe: predicated IMAD, in place)
+  const int b2 = km1 & 4, b1 = km1 & 2, b0 = km1 & 1;
+  // stage "shift by 4"
+  float x0 = psel(f[4], f[0], b2), x1 = psel(f[5], f[1], b2), x2 = psel(f[6], f[2], b2), x3 = psel(f[7], f[3], b2);
+  const float m2 = psel(INF, -0.0f, b2);
+  float x4 = f[4] + m2, x5 = f[5] + m2, x6 = f[6] + m2, x7 = f[7] + m2;
+  // stage "shift by 2"
   pmov_fma(x0, x2, b1, one); pmov_fma(x1, x3, b1, one); pmov_fma(x2, x4, b1, one); pmov_fma(x3, x5, b1, one);
   pmov_fma(x4, x6, b1, one); pmov_fma(x5, x7, b1, one); pinf_fma(x6, b1); pinf_fma(x7, b1);
   // stage "shift by 1"

@@ -268,13 +268,15 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     mbar_fence_init();
   }
   __syncthreads();
-  if (!TABG && threadIdx.x == 0) {
-    // stage the runtime table: TMA bulk copies of <= 32 KB each, one mbarrier phase
-    mbar_arrive_expect_tx(bar_tab, tab_bytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab);
-    for (uint32_t off = 0; off < tab_bytes; off += 32768u) {
-      uint32_t n = min(32768u, tab_bytes - off);
-      tma_bulk_g2s(smem + off, src + off, n, bar_tab);
+  if constexpr (!TABG) {
+    if (threadIdx.x == 0) {
+      // stage the runtime table: TMA bulk copies of <= 32 KB each, one mbarrier phase
+      mbar_arrive_expect_tx(bar_tab, tab_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab);
+      for (uint32_t off = 0; off < tab_bytes; off += 32768u) {
+        uint32_t n = min(32768u, tab_bytes - off);
+        tma_bulk_g2s(smem + off, src + off, n, bar_tab);
+      }
     }
   }
 
