@@ -68,6 +68,12 @@ typedef enum sb_status {
 #define SB_FLAG_INTEGER_STARTS 1u /* MILP start variables are Integer, milp.py:142-143 */
 #define SB_FLAG_REDUCED 2u        /* opt bytes carry s = 0; the min-over-strategies table is used
                                      (PerformanceEvaluator.py:101-115) */
+#define SB_FLAG_POST_KEY 8u       /* sb_eval: when the last candidate is scored, publish *best_key in this
+                                     rank's peer-visible mailbox (see sb_xchg_*); the same kernel does both */
+#define SB_FLAG_FOLD_PREV 16u     /* with SB_FLAG_POST_KEY: the kernel's prologue first MINs into *best_key the keys
+                                     all ranks published in the PREVIOUS round (one-round pipelined exchange:
+                                     the NVLink latency hides under the evaluation); finish with sb_xchg_reduce */
+#define SB_IPC_HANDLE_BYTES 64
 
 typedef struct sb_handle sb_handle;
 
@@ -137,6 +143,25 @@ int sb_eval_full(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, 
  * the cell), gpu count k, node index.  makespan (nullable) receives the candidate's makespan. */
 int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags, float* start,
               uint32_t* slotmask, uint8_t* strategy, uint8_t* gpus, uint8_t* node, float* makespan);
+
+/* ---- multi-GPU exchange over NVLink peer memory ----------------------------------------------
+ * The path shards by candidate id; its only exchange is one MIN of the packed 64-bit key per round.
+ * Each rank owns a mailbox in HBM that every peer maps with CUDA IPC; a rank publishes {key, round} in
+ * its own mailbox (release at system scope; fused into the tail of the evaluation kernel with
+ * SB_FLAG_POST_KEY) and a one-warp kernel on every rank loads all mailboxes over NVLink (acquire at
+ * system scope) until they show the round, then folds the MIN.  One process per GPU:
+ *   sb_xchg_create  -> 64-byte IPC handle; all-gather the handles (any transport);
+ *   sb_xchg_connect (all handles, rank order);
+ *   per round: sb_eval(..., flags | SB_FLAG_POST_KEY, ..., best_key, ...)  [or sb_xchg_post(key)]
+ *              sb_xchg_reduce(out, fold)   — every rank must post and reduce every round;
+ *   sb_xchg_check: synchronous; reports a timed-out wait (a peer never posted).
+ * There is no reference counterpart (the reference solver is a single CPU process). */
+int sb_xchg_create(sb_handle* h, int rank, int world, void* handle_out /* SB_IPC_HANDLE_BYTES */);
+int sb_xchg_connect(sb_handle* h, const void* handles /* [world][SB_IPC_HANDLE_BYTES] */);
+int sb_xchg_post(sb_handle* h, const uint64_t* key_dev);
+/* out_dev receives the MIN over all ranks; fold_dev (nullable) is MIN-ed with it in place */
+int sb_xchg_reduce(sb_handle* h, uint64_t* out_dev, uint64_t* fold_dev);
+int sb_xchg_check(sb_handle* h);
 
 /* ---- search (replaces prob.solve(), milp.py:321-327) ---------------------------------------
  * A population of `chains` candidates lives on the device.  sb_search_init seeds it (random

@@ -8,13 +8,17 @@ SO_PATH = os.environ.get("SATURN_B200_LIB") or os.path.join(_HERE, "libsaturn_b2
 
 FLAG_INTEGER_STARTS = 1
 FLAG_REDUCED = 2
+FLAG_POST_KEY = 8
+FLAG_FOLD_PREV = 16
+IPC_HANDLE_BYTES = 64
 _FLAG_FORCE_GENERIC = 0x80000000
 
 # every symbol include/saturn_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "sb_abi_version", "sb_last_error", "sb_create", "sb_destroy", "sb_sync", "sb_set_table",
     "sb_set_sentinel", "sb_get_reduced", "sb_eval", "sb_last_eval_path", "sb_validate", "sb_eval_host", "sb_eval_full",
-    "sb_decode", "sb_search_init", "sb_search_round", "sb_search_best_key_ptr", "sb_search_best",
+    "sb_decode", "sb_xchg_create", "sb_xchg_connect", "sb_xchg_post", "sb_xchg_reduce", "sb_xchg_check",
+    "sb_search_init", "sb_search_round", "sb_search_best_key_ptr", "sb_search_best",
     "sb_search_inject", "sb_search_resample", "sb_search_is_fused", "sb_search_stats",
 ]
 
@@ -58,6 +62,11 @@ def load():
         "sb_eval_host": [vp, vp, vp, i64, i64, u32, vp],
         "sb_eval_full": [vp, vp, vp, i64, i64, u32, vp, vp, vp],
         "sb_decode": [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp],
+        "sb_xchg_create": [vp, ci, ci, vp],
+        "sb_xchg_connect": [vp, vp],
+        "sb_xchg_post": [vp, vp],
+        "sb_xchg_reduce": [vp, vp, vp],
+        "sb_xchg_check": [vp],
         "sb_search_init": [vp, C.POINTER(SearchParams), vp, vp],
         "sb_search_round": [vp, ci],
         "sb_search_best_key_ptr": [vp, C.POINTER(vp)],

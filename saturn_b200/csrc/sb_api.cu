@@ -72,6 +72,13 @@ struct sb_handle {
   size_t dec_cap = 0;
   SearchState search;
   int last_path = -1;
+  // peer-memory exchange
+  XchgDev xd;
+  bool xchg_created = false, xchg_ready = false;
+  unsigned long long xseq = 0;
+  unsigned* d_xcounter = nullptr;
+  int* d_xerr = nullptr;
+  void* x_opened[kMaxRanks] = {nullptr};
 };
 
 static int use_device(sb_handle* h) {
@@ -102,6 +109,21 @@ static void free_staging(sb_handle* h) {
     h->st_o[i] = h->st_p[i] = nullptr; h->st_mk[i] = nullptr;
   }
   h->st_cap = 0;
+}
+
+static void free_xchg(sb_handle* h) {
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (h->x_opened[r]) cudaIpcCloseMemHandle(h->x_opened[r]);
+    h->x_opened[r] = nullptr;
+  }
+  cudaFree(h->xd.local);
+  cudaFree(h->d_xcounter);
+  cudaFree(h->d_xerr);
+  h->xd = XchgDev();
+  h->d_xcounter = nullptr;
+  h->d_xerr = nullptr;
+  h->xchg_created = h->xchg_ready = false;
+  h->xseq = 0;
 }
 
 extern "C" {
@@ -146,6 +168,7 @@ int sb_destroy(sb_handle* h) {
   free_search(h);
   free_table(h);
   free_staging(h);
+  free_xchg(h);
   cudaFree(h->d_scratch);
   cudaFree(h->dec_buf);
   for (int i = 0; i < 2; ++i)
@@ -272,7 +295,19 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
   c.best_key = reinterpret_cast<unsigned long long*>(best_key);
   c.id_base = id_base;
   c.force_generic = (flags & 0x80000000u) ? 1 : 0;  // test hooks: 0x80000000 generic kernel, 0x40000000 no streaming
+  const bool post = (flags & SB_FLAG_POST_KEY) != 0;
+  if (post) {
+    if (!h->xchg_ready) return fail(SB_ERR_STATE, "SB_FLAG_POST_KEY needs sb_xchg_connect first");
+    if (!best_key) return fail(SB_ERR_ARG, "SB_FLAG_POST_KEY needs best_key");
+    c.xp.x = h->xd;
+    c.xp.seq = ++h->xseq;
+    c.xp.counter = h->d_xcounter;
+    c.xp.fold_prev = (flags & SB_FLAG_FOLD_PREV) ? 1 : 0;
+    c.xp.error = h->d_xerr;
+  }
   CK(eval_launch(h->dev, c, h->stream, &h->last_path));
+  if (post && (h->last_path == 0 || B == 0))  // the generic kernel has no fused tail: post separately
+    CK(xchg_post_launch(h->xd, reinterpret_cast<unsigned long long*>(best_key), h->xseq, h->stream));
   return SB_OK;
 }
 
@@ -405,6 +440,89 @@ int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags
       strategy[j] = reduced ? h->h_args[static_cast<size_t>(j) * kSlots + col] : static_cast<uint8_t>(opt[j] >> 3);
   }
   if (makespan) *makespan = mk;
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ exchange
+int sb_xchg_create(sb_handle* h, int rank, int world, void* handle_out) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+    return fail(SB_ERR_ARG, "rank %d / world %d outside 0..%d", rank, world, kMaxRanks);
+  if (!handle_out) return fail(SB_ERR_ARG, "handle_out is null");
+  free_xchg(h);
+  const size_t bytes = 2 * kMaxRanks * 2 * sizeof(unsigned long long);
+  CK(cudaMalloc(&h->xd.local, bytes));
+  CK(cudaMemset(h->xd.local, 0, bytes));
+  CK(cudaMalloc(&h->d_xcounter, sizeof(unsigned)));
+  CK(cudaMemset(h->d_xcounter, 0, sizeof(unsigned)));
+  CK(cudaMalloc(&h->d_xerr, sizeof(int)));
+  CK(cudaMemset(h->d_xerr, 0, sizeof(int)));
+  h->xd.rank = rank;
+  h->xd.world = world;
+  cudaIpcMemHandle_t hdl;
+  CK(cudaIpcGetMemHandle(&hdl, h->xd.local));
+  static_assert(sizeof(hdl) == SB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &hdl, sizeof(hdl));
+  h->xchg_created = true;
+  return SB_OK;
+}
+
+int sb_xchg_connect(sb_handle* h, const void* handles) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (!h->xchg_created) return fail(SB_ERR_STATE, "sb_xchg_create has not been called");
+  if (!handles) return fail(SB_ERR_ARG, "handles is null");
+  const char* hp = static_cast<const char*>(handles);
+  for (int r = 0; r < h->xd.world; ++r) {
+    if (r == h->xd.rank) {
+      h->xd.peer[r] = h->xd.local;
+      continue;
+    }
+    cudaIpcMemHandle_t hdl;
+    memcpy(&hdl, hp + static_cast<size_t>(r) * SB_IPC_HANDLE_BYTES, sizeof(hdl));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+    h->x_opened[r] = p;
+    h->xd.peer[r] = static_cast<unsigned long long*>(p);
+  }
+  h->xchg_ready = true;
+  return SB_OK;
+}
+
+int sb_xchg_post(sb_handle* h, const uint64_t* key_dev) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (!h->xchg_ready) return fail(SB_ERR_STATE, "sb_xchg_connect has not been called");
+  if (!key_dev) return fail(SB_ERR_ARG, "key_dev is null");
+  ++h->xseq;
+  CK(xchg_post_launch(h->xd, reinterpret_cast<const unsigned long long*>(key_dev), h->xseq, h->stream));
+  return SB_OK;
+}
+
+int sb_xchg_reduce(sb_handle* h, uint64_t* out_dev, uint64_t* fold_dev) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (!h->xchg_ready) return fail(SB_ERR_STATE, "sb_xchg_connect has not been called");
+  if (!out_dev) return fail(SB_ERR_ARG, "out_dev is null");
+  if (h->xseq == 0) return fail(SB_ERR_STATE, "nothing has been posted yet");
+  CK(xchg_reduce_launch(h->xd, h->xseq, reinterpret_cast<unsigned long long*>(out_dev),
+                        reinterpret_cast<unsigned long long*>(fold_dev), h->d_xerr, h->stream));
+  return SB_OK;
+}
+
+int sb_xchg_check(sb_handle* h) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (!h->xchg_created) return fail(SB_ERR_STATE, "sb_xchg_create has not been called");
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, h->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (err) return fail(SB_ERR_CUDA, "peer exchange timed out waiting for a rank's post");
   return SB_OK;
 }
 

@@ -46,6 +46,7 @@ struct TileArgs {
   long long ntiles;
   int one;  // run-time 1 (see pmov_fma)
   SearchFuse sf;  // SEARCH variant only
+  XchgPost xp;    // xp.counter != nullptr: the last CTA to finish posts *best_key to every peer's mailbox
 };
 
 struct PrioChunk {
@@ -288,6 +289,37 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
   st.orow = tile_o + lane * a.row_o;
   st.ns = node_s + lane;
 
+  if (a.xp.counter != nullptr && a.xp.fold_prev && a.xp.seq > 1 && blockIdx.x == 0 && warp == 0) {
+    // pipelined exchange, prologue: fold the keys every rank published for the PREVIOUS round
+    // (lane r loads rank r's mailbox over NVLink, acquire at system scope) into best_key.  The 0.45 ms
+    // of evaluation that follows hides the NVLink latency; the publish of this round is in the tail.
+    const unsigned long long want = a.xp.seq - 1;
+    unsigned long long k = ~0ull;
+    bool ok = true;
+    if (lane < a.xp.x.world) {
+      const unsigned long long* slot = a.xp.x.peer[lane] + (want & 1ull) * 2;
+      unsigned long long seen;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(slot + 1) : "memory");
+        if (seen >= want) break;
+        __nanosleep(64);
+      } while (++spins < (1u << 22));
+      ok = seen >= want;
+      if (ok) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(k) : "l"(slot) : "memory");
+    }
+    ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, d);
+      k = o < k ? o : k;
+    }
+    if (lane == 0) {
+      if (!ok) *a.xp.error = 1;
+      else atomicMin(a.best_key, k);
+    }
+  }
+
   uint32_t phase = 0;
   bool tab_ready = TABG;
   for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
@@ -391,6 +423,24 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b0 + lane), lane);
   }
   if (!tab_ready && threadIdx.x == 0) mbar_wait(bar_tab, 0);  // never leave a bulk copy in flight
+  if (a.xp.counter != nullptr) {
+    // fused exchange: the CTA that finishes last has seen every atomicMin on best_key; it publishes
+    // {key, round} in this rank's mailbox (local stores, release at system scope).  Peers read the
+    // mailbox over NVLink in k_xchg_reduce (sb_xchg.cu).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned done = atomicAdd(a.xp.counter, 1u);
+      if (done == gridDim.x - 1) {
+        *a.xp.counter = 0;
+        __threadfence();
+        const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(a.best_key);
+        unsigned long long* slot = a.xp.x.local + (a.xp.seq & 1ull) * 2;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(k) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(a.xp.seq) : "memory");
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -665,6 +715,7 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
     a.out = c.out; a.best_key = c.best_key; a.id_base = c.id_base;
     a.ntiles = (c.B + 31) / 32;
     a.one = 1;
+    a.xp = c.xp;
     if (path_used) *path_used = tabg ? 4 : (stream ? 3 : (a.use_bulk ? 2 : 1));
     if (tabg) {
       if (pb == 1) return ints ? launch_tiles<1, true, true, false, true>(dev, a, tp, st) : launch_tiles<1, false, true, false, true>(dev, a, tp, st);

@@ -13,6 +13,24 @@ struct Device {
   size_t smem_optin = 0;  // max dynamic shared memory per CTA (227 KB on B200)
 };
 
+// peer-memory MIN exchange (sb_xchg.cu)
+constexpr int kMaxRanks = 16;
+struct XchgDev {
+  int rank = 0, world = 1;
+  unsigned long long* local = nullptr;            // our mailbox: [2 parities][2] u64 = {key, round}
+  unsigned long long* peer[kMaxRanks] = {nullptr};  // every rank's mailbox mapped here (peer[rank] == local)
+};
+struct XchgPost {
+  XchgDev x;
+  unsigned long long seq = 0;
+  unsigned* counter = nullptr;  // CTA completion counter (zero between launches); null = no fused post
+  int fold_prev = 0;            // prologue: fold the peers' keys of round seq-1 into best_key (pipelined exchange)
+  int* error = nullptr;         // set to 1 if a peer's round never shows up
+};
+cudaError_t xchg_post_launch(const XchgDev& x, const unsigned long long* key, unsigned long long seq, cudaStream_t st);
+cudaError_t xchg_reduce_launch(const XchgDev& x, unsigned long long seq, unsigned long long* out,
+                               unsigned long long* fold, int* error, cudaStream_t st);
+
 struct TilePlan {
   int warps = 0;
   int row_o = 0, row_p = 0, copy_o = 0, copy_p = 0;
@@ -32,6 +50,7 @@ struct EvalCall {
   unsigned long long* best_key = nullptr;
   uint32_t id_base = 0;
   int force_generic = 0;
+  XchgPost xp;  // fused post of best_key at the end of the tile kernel (tile paths only)
 };
 
 // what the fused search round needs besides an EvalCall (see k_eval_tiles<..., SEARCH = true>)

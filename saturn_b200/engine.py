@@ -122,13 +122,14 @@ class Engine:
 
     def eval(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False,
              out: Optional[torch.Tensor] = None, best_key: Optional[torch.Tensor] = None, id_base: int = 0,
-             _force_generic: bool = False, _no_stream: bool = False) -> torch.Tensor:
+             _force_generic: bool = False, _no_stream: bool = False, post_key: bool = False, fold_prev: bool = False) -> torch.Tensor:
         """Makespan of every candidate (device tensors).  Asynchronous on the handle's stream."""
         B, stride = self._check_cands(opt, prio, True)
         if out is None:
             out = torch.empty(B, dtype=torch.float32, device=self.device)
         fl = _flags(integer_starts, reduced) | (_lib._FLAG_FORCE_GENERIC if _force_generic else 0) | (
-            0x40000000 if _no_stream else 0)
+            0x40000000 if _no_stream else 0) | (_lib.FLAG_POST_KEY if post_key else 0) | (
+            _lib.FLAG_FOLD_PREV if (post_key and fold_prev) else 0)
         kp = C.c_void_p(best_key.data_ptr()) if best_key is not None else None
         check(self._lib.sb_eval(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride, fl,
                                 C.c_void_p(out.data_ptr()), kp, id_base & 0xffffffff))
@@ -184,6 +185,40 @@ class Engine:
                                   C.c_void_p(gpus.ctypes.data), C.c_void_p(node.ctypes.data), C.byref(mk)))
         return {"start": start, "slotmask": mask, "strategy": strat, "gpus": gpus, "node": node,
                 "makespan": float(mk.value)}
+
+    # ------------------------------------------------------------------ multi-GPU exchange (NVLink peer memory)
+    def xchg_init(self, dist) -> bool:
+        """Set up the peer-memory MIN exchange over the ranks of an initialised torch.distributed
+        group (one process per GPU of one node).  The 64-byte CUDA IPC handles are all-gathered with
+        the group itself; returns False (and leaves the engine on the NCCL path) if a peer mapping
+        cannot be opened."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        hdl = np.zeros(_lib.IPC_HANDLE_BYTES, dtype=np.uint8)
+        check(self._lib.sb_xchg_create(self._h, rank, world, C.c_void_p(hdl.ctypes.data)))
+        mine = torch.from_numpy(hdl).to(self.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        flat = torch.stack(allh).cpu().numpy().copy()
+        rc = self._lib.sb_xchg_connect(self._h, C.c_void_p(flat.ctypes.data))
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)           # all ranks or none
+        self._xchg = bool(ok.item())
+        return self._xchg
+
+    @property
+    def has_xchg(self) -> bool:
+        return getattr(self, "_xchg", False)
+
+    def xchg_post(self, key: torch.Tensor):
+        check(self._lib.sb_xchg_post(self._h, C.c_void_p(key.data_ptr())))
+
+    def xchg_reduce(self, out: torch.Tensor, fold: Optional[torch.Tensor] = None):
+        """out[0] = MIN over all ranks of the keys posted this round; `fold` is MIN-ed in place."""
+        check(self._lib.sb_xchg_reduce(self._h, C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(fold.data_ptr()) if fold is not None else None))
+
+    def xchg_check(self):
+        check(self._lib.sb_xchg_check(self._h))
 
     # ------------------------------------------------------------------ search
     def search_init(self, chains: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,

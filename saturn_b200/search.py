@@ -110,7 +110,15 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     done_rounds = 0
     stop = torch.zeros(1, dtype=torch.int32, device=engine.device)
 
+    use_xchg = bool(dist) and getattr(engine, "has_xchg", False)
+
     def exchange() -> int:
+        if use_xchg:
+            # NVLink peer-memory MIN: every rank stores its key into every peer's mailbox
+            engine.xchg_post(local_key)
+            engine.xchg_reduce(gkey)
+            engine.sync()
+            return int(gkey.item())
         engine.sync()
         gkey.copy_(local_key)
         if dist:
