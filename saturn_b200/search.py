@@ -110,6 +110,12 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     done_rounds = 0
     stop = torch.zeros(1, dtype=torch.int32, device=engine.device)
 
+    if dist and not getattr(engine, "has_xchg", False) and hasattr(engine, "xchg_init") \
+            and dist.get_backend() == "nccl":
+        try:
+            engine.xchg_init(dist)          # NVLink peer-memory mailboxes; stays on NCCL if it cannot map peers
+        except Exception:
+            pass
     use_xchg = bool(dist) and getattr(engine, "has_xchg", False)
 
     def exchange() -> int:
