@@ -349,3 +349,33 @@ def test_large_table_in_global_memory(engine):
     ref = c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy().astype(np.uint16), True, np.float32, threads=8)
     assert np.array_equal(a.cpu().numpy(), ref)
     assert torch.equal(a, engine.eval(opt, prio, _force_generic=True))
+
+
+def test_error_paths_and_unpadded_host_buffers(engine):
+    from saturn_b200._lib import SaturnB200Error
+    from saturn_b200.engine import Engine
+    fresh = Engine(0)
+    o = torch.zeros((4, 8), dtype=torch.uint8, device=fresh.device)
+    with pytest.raises((SaturnB200Error, ValueError)):
+        fresh.eval(o, o)                                            # no table yet
+    with pytest.raises(SaturnB200Error):
+        fresh.set_table(np.ones((4, 1, 9), dtype=np.float32))        # G > 8
+    with pytest.raises(SaturnB200Error):
+        fresh.set_table(np.ones((4, 1, 2), dtype=np.float32), [1, 9])  # gpu count 9
+    with pytest.raises(SaturnB200Error):
+        fresh.set_table(np.ones((4, 1, 2), dtype=np.float32), nodes=9)
+    fresh.close()
+    J, S, G, B = 100, 3, 8, 5000
+    T, valid = R.synth_table(J, S, G, seed=8)
+    engine.set_table(T)
+    tab = R.canon_table(T, range(1, 9))
+    opt_h, prio_h = random_candidates(engine, B, valid, seed=9, device="cpu")
+    opt_c, prio_c = opt_h.contiguous(), prio_h.contiguous()        # row stride 100 bytes, pageable memory
+    out = engine.eval_host(opt_c, prio_c, out=torch.empty(B, dtype=torch.float32))
+    assert engine.last_eval_path() == 1
+    ref = c_oracle.evaluate(tab, opt_c.numpy(), prio_c.numpy(), True, np.float32, threads=8)
+    assert np.array_equal(out.numpy(), ref)
+    with pytest.raises(TypeError):
+        engine.eval(opt_h.to(engine.device).to(torch.int32), prio_h.to(engine.device))
+    with pytest.raises(ValueError):
+        engine.eval(opt_h.to(engine.device)[:, :50], prio_h.to(engine.device)[:, :50])
