@@ -129,7 +129,7 @@ def cpu_eval_rate(threads, seconds_target=12.0, seed=0):
     t0 = time.perf_counter()
     c_oracle.evaluate(tab, opt, prio, True, np.float32, threads=threads)
     dt = time.perf_counter() - t0
-    n = int(min(max(20000, 20000 * seconds_target / max(dt, 1e-3)), 4_000_000))
+    n = int(min(max(20000, 20000 * seconds_target / max(dt, 1e-3)), 16_000_000))
     reps = max(1, n // 20000)
     t0 = time.perf_counter()
     for _ in range(reps):
