@@ -71,14 +71,30 @@ struct LaneState {
   int SG;
   int one;
   float4* ns;  // MULTI: lane-private node-state column; node n lives at ns[(2n)*32], ns[(2n+1)*32]
+  int cur;     // MULTI: the node whose state is currently in f[] (its shared-memory copy is stale)
 
   __device__ __forceinline__ void reset(int nodes) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = 0.f;
     mk = 0.f;
+    cur = 0;
     if (MULTI) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int n = 0; n < 2 * nodes; ++n) ns[n * 32] = z;
+    }
+  }
+  // MULTI: bring node n's sorted state into the registers (write the previous node's back first).
+  // Lanes whose job stays on the same node as their previous job skip the shared-memory round trip.
+  __device__ __forceinline__ void switch_node(int n) {
+    if (n != cur) {
+      float4* old = ns + (2 * cur) * 32;
+      old[0] = make_float4(f[0], f[1], f[2], f[3]);
+      old[32] = make_float4(f[4], f[5], f[6], f[7]);
+      const float4* slot = ns + (2 * n) * 32;
+      const float4 lo = slot[0], hi = slot[32];
+      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
+      f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+      cur = n;
     }
   }
   // the two look-ups of a step (opt byte, then runtime) do not depend on the slot state, so callers
@@ -91,13 +107,8 @@ struct LaneState {
     if (!MULTI) {
       ls_step<INT>(f, mk, rt, o & 7, one);
     } else {
-      float4* slot = ns + (2 * (o >> 3)) * 32;
-      const float4 lo = slot[0], hi = slot[32];
-      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
-      f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+      switch_node(o >> 3);
       ls_step<INT, true>(f, mk, rt, o & 7, one);
-      slot[0] = make_float4(f[0], f[1], f[2], f[3]);
-      slot[32] = make_float4(f[4], f[5], f[6], f[7]);
     }
   }
   __device__ __forceinline__ void step(int j) {
@@ -106,15 +117,10 @@ struct LaneState {
       const float rt = tab[j * SG + o];
       ls_step<INT>(f, mk, rt, o & 7, one);
     } else {
-      const int col = o & 7, n = o >> 3;  // reduced table only: opt = (node << 3) | (k - 1)
+      const int col = o & 7;  // reduced table only: opt = (node << 3) | (k - 1)
       const float rt = tab[j * 8 + col];
-      float4* slot = ns + (2 * n) * 32;
-      const float4 lo = slot[0], hi = slot[32];
-      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
-      f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+      switch_node(o >> 3);
       ls_step<INT, true>(f, mk, rt, col, one);
-      slot[0] = make_float4(f[0], f[1], f[2], f[3]);
-      slot[32] = make_float4(f[4], f[5], f[6], f[7]);
     }
   }
   __device__ __forceinline__ float result() const { return (INT || MULTI) ? mk : f[7]; }
