@@ -102,7 +102,9 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
  * search (it is still evaluated like any number if a caller's candidate selects it).  Default 1e6;
  * pass +inf to treat every finite cell as usable.  Takes effect at the next sb_set_table. */
 int sb_set_sentinel(sb_handle* h, float threshold);
-/* copy the reduced table back (host pointers, either may be NULL): tmin fp32 [J][8], args u8 [J][8] */
+/* copy the reduced table back (host pointers, either may be NULL): tmin fp32 [J][8], args u8 [J][8].
+ * This is the table the reference solver is actually given: Task.strategies[g] after the profiler's
+ * min over executors (PerformanceEvaluator.py:101-115), read at milp.py:77-81. */
 int sb_get_reduced(sb_handle* h, float* tmin, uint8_t* args);
 
 /* ---- the measured kernel: makespan of B candidates ----------------------------------------
@@ -127,18 +129,22 @@ int sb_validate(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, i
                 unsigned flags, int64_t* bad_rows);
 
 /* same through HOST buffers: chunked H2D copies, kernel, D2H of the makespans, pipelined on
- * two internal streams; returns when makespan_out (host) is complete. */
+ * two internal streams; returns when makespan_out (host) is complete.  This is the call shape a CPU
+ * caller of the reference has (everything in host memory, milp.py:23). */
 int sb_eval_host(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
                  unsigned flags, float* makespan_out);
 
 /* ---- full plan of B candidates (slot-exact; used for decode and for parity tests) ---------
+ * Replaces reading the start / occupancy variables back from the solved MILP: sta[n][g][t] and
+ * tga[t][n][g] of milp.py:330-334 (one shared Integer start per task, milp.py:139-149,233-256).
  * start_out fp32 [B][J] and slotmask_out u32 [B][J] are indexed by JOB; bit g (g < 8) of the mask =
  * GPU slot g of the job's node, bits 16.. = node index.  Device pointers; start_out / slotmask_out
  * may be NULL. */
 int sb_eval_full(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride,
                  unsigned flags, float* makespan_out, float* start_out, uint32_t* slotmask_out);
 
-/* decode ONE candidate given in host memory into host arrays (all [J]; any may be NULL):
+/* decode ONE candidate given in host memory into host arrays (all [J]; any may be NULL) — everything
+ * milp.py:330-352 extracts per task (start, occupied GPUs, selected option, node):
  * start, GPU mask within the node, strategy index s (for SB_FLAG_REDUCED the arg-min strategy of
  * the cell), gpu count k, node index.  makespan (nullable) receives the candidate's makespan. */
 int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags, float* start,
