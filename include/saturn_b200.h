@@ -200,9 +200,11 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
 /* tournament resampling: every chain continues from a random rival's candidate if the rival's
  * current makespan is strictly better (keeps the population concentrated on good basins) */
 int sb_search_resample(sb_handle* h);
-/* 1 if rounds run as ONE fused kernel (move + evaluate + accept on shared-memory rows; needs both rows
- * of 32 candidates x >= 4 warps to fit beside the table), 0 if they run as propose / evaluate / accept
- * kernels (large J).  Both are the same Metropolis search; moves and RNG streams differ slightly. */
+/* 1 if rounds run as ONE fused kernel (move + evaluate + accept), 0 if they run as propose / evaluate /
+ * accept kernels.  Fused rounds keep both rows of a tile's 32 candidates in shared memory when they fit
+ * (all moves); for larger J only the opt rows are resident and the prio rows stream through registers,
+ * with swaps applied to the stream on the fly (no re-insertion moves).  All forms are the same
+ * Metropolis search; move mixes and RNG streams differ slightly. */
 int sb_search_is_fused(sb_handle* h);
 /* candidates evaluated so far by this handle's searches */
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);

@@ -611,7 +611,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   s.scale = isfinite(mk) ? mk : 1.0f;
   s.evaluated = d.chains;
   s.rounds_done = 0;
-  s.fused_ok = !(p->flags & 0x20000000u) && search_round_fits(h->dev, J, (reduced ? 1 : h->S) * kSlots, h->nodes);
+  s.fused_ok = !(p->flags & 0x20000000u) && (search_round_mode(h->dev, J, (reduced ? 1 : h->S) * kSlots, h->nodes) != 0);
   return SB_OK;
 }
 

@@ -152,6 +152,7 @@ __device__ __forceinline__ void fold_best(unsigned long long* best_key, bool act
 struct Move {
   int kind;  // 0 none, 1 opt byte of job a changed, 2 positions a,b swapped, 3 positions [a..b] rewritten
   int a, b;
+  int va, vb;  // kind 2 on streamed prio rows: the jobs that were at positions a and b
 };
 
 __device__ __forceinline__ uint32_t bounded32(uint64_t r, uint32_t n) {
@@ -168,10 +169,14 @@ __device__ __forceinline__ void smem_prio_st(uint8_t* row, int i, int v) {
   else reinterpret_cast<uint16_t*>(row)[i] = static_cast<uint16_t>(v);
 }
 
-template <int PB>
-__device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t gid, uint8_t* orow, uint8_t* prow) {
+// `prow` is the lane's prio row in SHARED memory (non-streaming variant: the move is applied in place) or,
+// with STREAMED = true, its row in GLOBAL memory (read-only here: a swap is applied on the fly to the
+// chunks as they stream through registers, see patch_chunk; re-insertion moves are not proposed).
+template <int PB, bool STREAMED>
+__device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t gid, uint8_t* orow, const uint8_t* prow_c) {
+  uint8_t* prow = const_cast<uint8_t*>(prow_c);
   Move m;
-  m.kind = 0; m.a = 0; m.b = 0;
+  m.kind = 0; m.a = 0; m.b = 0; m.va = 0; m.vb = 0;
   const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * sf.round + 0);
   const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * sf.round + 1);
   const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * sf.round + 2);
@@ -202,13 +207,15 @@ __device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t
   }
   if (J < 2) return m;
   const int a = bounded32(r1, J);
-  if (kind < 70) {  // swap two priorities
+  if (STREAMED || kind < 70) {  // swap two priorities
     int b = bounded32(r2, J - 1);
     if (b >= a) ++b;
     const int va = smem_prio_ld<PB>(prow, a), vb = smem_prio_ld<PB>(prow, b);
-    smem_prio_st<PB>(prow, a, vb);
-    smem_prio_st<PB>(prow, b, va);
-    m.kind = 2; m.a = a; m.b = b;
+    if (!STREAMED) {
+      smem_prio_st<PB>(prow, a, vb);
+      smem_prio_st<PB>(prow, b, va);
+    }
+    m.kind = 2; m.a = a; m.b = b; m.va = va; m.vb = vb;
     return m;
   }
   // re-insert the job at position a up to 48 places earlier or later
@@ -235,10 +242,11 @@ __device__ __forceinline__ void write_back(const Move& m, const uint8_t* orow, c
   if (m.kind == 1) {
     go[m.a] = orow[m.a];
   } else if (m.kind == 2) {
-    if (PB == 1) { gp[m.a] = prow[m.a]; gp[m.b] = prow[m.b]; }
+    // positions a and b exchange their jobs (values carried in the move: valid for both variants)
+    if (PB == 1) { gp[m.a] = static_cast<uint8_t>(m.vb); gp[m.b] = static_cast<uint8_t>(m.va); }
     else {
-      reinterpret_cast<uint16_t*>(gp)[m.a] = reinterpret_cast<const uint16_t*>(prow)[m.a];
-      reinterpret_cast<uint16_t*>(gp)[m.b] = reinterpret_cast<const uint16_t*>(prow)[m.b];
+      reinterpret_cast<uint16_t*>(gp)[m.a] = static_cast<uint16_t>(m.vb);
+      reinterpret_cast<uint16_t*>(gp)[m.b] = static_cast<uint16_t>(m.va);
     }
   } else if (m.kind == 3) {
     for (int i = m.a; i <= m.b; ++i) {
@@ -248,11 +256,26 @@ __device__ __forceinline__ void write_back(const Move& m, const uint8_t* orow, c
   }
 }
 
+// Streamed prio rows: overwrite schedule position `pos` with job `val` in the 256-bit chunk `c` held in
+// registers (no dynamic register indexing: the word is selected by predication over the 8 words).
+template <int PB>
+__device__ __forceinline__ void patch_chunk(PrioChunk& q, int c, int pos, int val) {
+  constexpr int STEPS = 32 / PB;
+  if (pos / STEPS != c) return;
+  const int t = pos % STEPS;
+  const int widx = PB == 1 ? (t >> 2) : (t >> 1);
+  const int sh = PB == 1 ? (t & 3) * 8 : (t & 1) * 16;
+  const uint32_t mask = (PB == 1 ? 0xffu : 0xffffu) << sh;
+  const uint32_t ins = static_cast<uint32_t>(val) << sh;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i == widx) q.w[i] = (q.w[i] & ~mask) | ins;
+}
+
 // TABG: the runtime table stays in global memory (read through L1/L2) — for tables larger than the
 // shared memory left beside the opt tiles (e.g. J = 1024 with 8 strategies: 256 KB).
 template <int PB, bool INT, bool STREAM, bool MULTI, bool SEARCH = false, bool TABG = false>
 __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const TileArgs a) {
-  static_assert(!(SEARCH && STREAM), "the fused search round mutates shared-memory rows");
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -367,8 +390,8 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     Move mv;
     mv.kind = 0; mv.a = 0; mv.b = 0;
     if (SEARCH && active)
-      mv = apply_move<PB>(a.sf, a.J, a.sf.chain_base + static_cast<uint64_t>(b0 + lane), tile_o + lane * a.row_o,
-                          tile_p + lane * a.row_p);
+      mv = apply_move<PB, STREAM>(a.sf, a.J, a.sf.chain_base + static_cast<uint64_t>(b0 + lane),
+                                  tile_o + lane * a.row_o, STREAM ? pg : tile_p + lane * a.row_p);
     if (active) {
       st.reset(a.nodes);
       const int J = a.J;
@@ -378,6 +401,10 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         for (int c = 0; c < nch; ++c) {
           PrioChunk nxt = q;
           if (c + 1 < nch) nxt = ld_prio32(pg + (c + 1) * 32);
+          if (SEARCH && mv.kind == 2) {  // the proposed swap, applied to the stream
+            patch_chunk<PB>(q, c, mv.a, mv.vb);
+            patch_chunk<PB>(q, c, mv.b, mv.va);
+          }
           if ((c + 1) * STEPS <= J) {
 #pragma unroll
             for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(q.w, t));
@@ -747,7 +774,8 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
 // cudaErrorNotSupported when the shared-memory tiles (both rows resident, >= 4 warps) do not fit;
 // the caller then runs the unfused propose / evaluate / accept round.
 template <int PB, bool INT>
-static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const TilePlan& tp, bool multi, cudaStream_t st) {
+static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const TilePlan& tp, bool multi, bool stream,
+                                   cudaStream_t st) {
   auto launch = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
     if (e != cudaSuccess) return e;
@@ -756,14 +784,22 @@ static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const T
     kern<<<grid, tp.warps * 32, tp.smem, st>>>(a);
     return cudaGetLastError();
   };
+  if (stream) {
+    if (multi) return launch(k_eval_tiles<PB, INT, true, true, true>);
+    return launch(k_eval_tiles<PB, INT, true, false, true>);
+  }
   if (multi) return launch(k_eval_tiles<PB, INT, false, true, true>);
   return launch(k_eval_tiles<PB, INT, false, false, true>);
 }
 
-bool search_round_fits(const Device& dev, int J, int SG, int nodes) {
+// 2 = both rows resident (all moves), 1 = opt rows resident + prio streamed (large J: no re-insertion
+// moves), 0 = neither fits: unfused rounds
+int search_round_mode(const Device& dev, int J, int SG, int nodes) {
   const int pb = J <= 256 ? 1 : 2;
   TilePlan tp;
-  return plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 4;
+  if (plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 4) return 2;
+  if (plan_tiles(dev, J, SG, pb, true, nodes, &tp) >= 2) return 1;
+  return 0;
 }
 
 cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st) {
@@ -773,8 +809,12 @@ cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const Sear
   const bool bulk_ok = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0);
   TilePlan tp;
-  const int nw = plan_tiles(dev, c.J, c.SG, pb, false, c.nodes, &tp);
-  if (nw < 4 || !bulk_ok || c.stride_o < tp.copy_o || c.stride_p < tp.copy_p) return cudaErrorNotSupported;
+  const int mode = search_round_mode(dev, c.J, c.SG, c.nodes);
+  const bool stream = mode == 1;
+  if (mode == 0 || !bulk_ok) return cudaErrorNotSupported;
+  plan_tiles(dev, c.J, c.SG, pb, stream, c.nodes, &tp);
+  if (c.stride_o < tp.copy_o || c.stride_p < (stream ? ((c.J * pb + 31) & ~31) : tp.copy_p)) return cudaErrorNotSupported;
+  if (stream && (c.stride_p % 32 != 0 || reinterpret_cast<uintptr_t>(c.prio) % 32 != 0)) return cudaErrorNotSupported;
   TileArgs a;
   a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
   a.stride_o = c.stride_o; a.stride_p = c.stride_p;
@@ -785,8 +825,11 @@ cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const Sear
   a.ntiles = (c.B + 31) / 32;
   a.one = 1;
   a.sf = sf;
-  if (pb == 1) return ints ? dispatch_search<1, true>(dev, a, tp, c.nodes > 1, st) : dispatch_search<1, false>(dev, a, tp, c.nodes > 1, st);
-  return ints ? dispatch_search<2, true>(dev, a, tp, c.nodes > 1, st) : dispatch_search<2, false>(dev, a, tp, c.nodes > 1, st);
+  if (pb == 1)
+    return ints ? dispatch_search<1, true>(dev, a, tp, c.nodes > 1, stream, st)
+                : dispatch_search<1, false>(dev, a, tp, c.nodes > 1, stream, st);
+  return ints ? dispatch_search<2, true>(dev, a, tp, c.nodes > 1, stream, st)
+              : dispatch_search<2, false>(dev, a, tp, c.nodes > 1, stream, st);
 }
 
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st) {

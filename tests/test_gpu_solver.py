@@ -143,7 +143,7 @@ def test_multi_node_solve_matches_reference_milp(golden_n2):
         assert again[5] <= mk * (1 + 1e-9)
 
 
-@pytest.mark.parametrize("J,S,nodes", [(64, 6, 1), (256, 8, 1), (100, 1, 2), (400, 1, 1)])
+@pytest.mark.parametrize("J,S,nodes", [(64, 6, 1), (256, 8, 1), (100, 1, 2), (400, 1, 1), (1024, 1, 1), (700, 1, 2)])
 def test_fused_and_unfused_search_rounds(engine, J, S, nodes):
     """The fused round (move + evaluate + accept in one kernel) and the propose / evaluate / accept
     round are the same search: both improve on the seeded population, both return candidates whose
@@ -153,20 +153,20 @@ def test_fused_and_unfused_search_rounds(engine, J, S, nodes):
     T, valid = R.synth_table(J, S, 8, seed=2, masked=(S > 1))
     engine.set_table(T, nodes=nodes)
     tab = R.canon_table(T, range(1, 9))
-    reduced = nodes > 1
+    reduced = nodes > 1 or J > 400
     if reduced:
         tab = R.reduce_table(tab)[0][:, None, :]
     res = {}
     for fused in (True, False):
-        r = run_search(engine, chains=8192, rounds=40, seed=3, reduced=reduced, record_history=True, use_dist=False,
-                       _no_fused=not fused)
+        r = run_search(engine, chains=8192 if J <= 400 else 2048, rounds=40, seed=3, reduced=reduced or J > 400,
+                       record_history=True, use_dist=False, _no_fused=not fused)
         assert engine.search_is_fused() == fused
         assert r.history[-1][2] < r.history[0][2]
         mk = R.list_schedule(tab, r.opt, r.prio, True, np.float32, nodes=nodes)[0]
         assert mk == r.makespan
         assert sorted(r.prio.tolist()) == list(range(J))
         res[fused] = r.makespan
-    assert abs(res[True] / res[False] - 1) < 0.02
+    assert abs(res[True] / res[False] - 1) < (0.02 if J <= 400 else 0.05)
 
 
 @pytest.mark.parametrize("J,chains", [(1, 1), (2, 5), (3, 33), (7, 64)])
