@@ -306,8 +306,13 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
     c.xp.error = h->d_xerr;
   }
   CK(eval_launch(h->dev, c, h->stream, &h->last_path));
-  if (post && (h->last_path == 0 || B == 0))  // the generic kernel has no fused tail: post separately
+  if (post && (h->last_path == 0 || B == 0)) {
+    // the generic kernel has neither the fused prologue nor the fused tail: do both with the small kernels
+    if (c.xp.fold_prev && h->xseq > 1)
+      CK(xchg_reduce_launch(h->xd, h->xseq - 1, h->d_scratch + 1, reinterpret_cast<unsigned long long*>(best_key),
+                            h->d_xerr, h->stream));
     CK(xchg_post_launch(h->xd, reinterpret_cast<unsigned long long*>(best_key), h->xseq, h->stream));
+  }
   return SB_OK;
 }
 

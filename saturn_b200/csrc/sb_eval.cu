@@ -52,12 +52,23 @@ struct TileArgs {
 struct PrioChunk {
   uint32_t w[8];  // 32 bytes = 32 (u8) or 16 (u16) schedule positions
 };
+// kReadOnly: the rows are not written during the kernel (evaluation) -> non-coherent path; the fused
+// search round writes accepted moves back into the same rows, so it uses the coherent form.
+template <bool kReadOnly>
 __device__ __forceinline__ PrioChunk ld_prio32(const uint8_t* p) {
   PrioChunk c;
-  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]),
-                 "=r"(c.w[7])
-               : "l"(p));
+  if (kReadOnly) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]),
+                   "=r"(c.w[7])
+                 : "l"(p));
+  } else {
+    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]),
+                   "=r"(c.w[7])
+                 : "l"(p)
+                 : "memory");
+  }
   return c;
 }
 
@@ -369,7 +380,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + (b0 + lane) * a.stride_o, a.copy_o, bar_w);
         if (!STREAM) tma_bulk_g2s(tile_p + lane * a.row_p, pg, a.copy_p, bar_w);
       }
-      if (STREAM && active) q = ld_prio32(pg);  // overlaps the TMA wait
+      if (STREAM && active) q = ld_prio32<!SEARCH>(pg);  // overlaps the TMA wait
       mbar_wait(bar_w, phase);
       phase ^= 1;
     } else {
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         const int nch = (J + STEPS - 1) / STEPS;
         for (int c = 0; c < nch; ++c) {
           PrioChunk nxt = q;
-          if (c + 1 < nch) nxt = ld_prio32(pg + (c + 1) * 32);
+          if (c + 1 < nch) nxt = ld_prio32<!SEARCH>(pg + (c + 1) * 32);
           if (SEARCH && mv.kind == 2) {  // the proposed swap, applied to the stream
             patch_chunk<PB>(q, c, mv.a, mv.vb);
             patch_chunk<PB>(q, c, mv.b, mv.va);
