@@ -347,6 +347,24 @@ def main():
                      "makespan": plan[5], "h2d_bytes": int(J * 8 * 4), "d2h_bytes": int(J * (8 + 4 + 1 + 1 + 1)),
                      "api": "saturn.solver.solve(task_list) -> (sta, tga, bss, bna, boa, makespan); per rank"}
 
+    # ---- one fused search round at a large population (diagnostic: the kernel the solver actually runs)
+    search_leg = None
+    if not args.no_e2e and args.config == "C4":
+        chains = 1 << 20
+        eng.search_init(chains, seed=rank, chain_base=rank * chains, integer_starts=ints, reduced=False,
+                        t_start=5e-4, t_end=1e-6, total_rounds=64)
+        eng.search_round(4)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        eng.search_round(16)
+        s1.record()
+        torch.cuda.synchronize()
+        ms = s0.elapsed_time(s1) / 16
+        search_leg = {"candidates_per_s_per_gpu": chains / (ms * 1e-3), "ms_per_round": ms, "chains_per_gpu": chains,
+                      "fused": eng.search_is_fused(),
+                      "what": "propose + evaluate + Metropolis accept of every chain, one kernel per round"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         alg = B * bytes_per_candidate(J)
@@ -381,7 +399,7 @@ def main():
                                          "one MIN of a uint64 per step over NVLink peer memory (publish fused into the "
                                          "evaluation kernel, one-warp fold kernel)") if use_xchg else
                                         "one NCCL all_reduce(MIN) of a uint64 per step")},
-                "clocks": clocks, "e2e": e2e, "solve_api": solve_leg, "gpu_launches": args.steps, "roofline": roof,
+                "clocks": clocks, "e2e": e2e, "solve_api": solve_leg, "search_round": search_leg, "gpu_launches": args.steps, "roofline": roof,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
