@@ -219,9 +219,9 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     nodes = int(nodes)
     eng.set_table(Tdev, list(range(1, NSLOT + 1)), sentinel=float("inf"), nodes=nodes)
     if chains is None:
-        chains = int(os.environ.get("SATURN_B200_CHAINS", 1 << 16))
+        chains = int(os.environ.get("SATURN_B200_CHAINS", 1 << 17))
     if rounds is None:
-        rounds = int(os.environ.get("SATURN_B200_ROUNDS", 300))
+        rounds = int(os.environ.get("SATURN_B200_ROUNDS", 400))
     budget = float(os.environ.get("SATURN_B200_BUDGET_S", 20.0))
     try:
         budget = min(budget, float(timeout))
