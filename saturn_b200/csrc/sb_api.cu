@@ -532,6 +532,23 @@ int sb_xchg_check(sb_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------ search
+// Job-indexed opt row (the ABI's encoding) <-> opt by schedule position (position-major populations).
+static void opt_to_positions(int J, int pb, const uint8_t* opt, const void* prio, std::vector<uint8_t>* out) {
+  out->resize(J);
+  for (int i = 0; i < J; ++i) {
+    const int j = pb == 1 ? static_cast<const uint8_t*>(prio)[i] : static_cast<const uint16_t*>(prio)[i];
+    (*out)[i] = j < J ? opt[j] : 0;
+  }
+}
+
+static void opt_from_positions(int J, int pb, uint8_t* opt, const void* prio) {
+  std::vector<uint8_t> by_pos(opt, opt + J);
+  for (int i = 0; i < J; ++i) {
+    const int j = pb == 1 ? static_cast<const uint8_t*>(prio)[i] : static_cast<const uint16_t*>(prio)[i];
+    if (j < J) opt[j] = by_pos[i];
+  }
+}
+
 static int search_alloc(SearchState& s, void** p, size_t bytes) {
   if (s.nblocks >= 16) return fail(SB_ERR_NOMEM, "search block table full");
   cudaError_t e = cudaMalloc(p, bytes);
@@ -542,6 +559,15 @@ static int search_alloc(SearchState& s, void** p, size_t bytes) {
 
 static int search_eval(sb_handle* h, bool cur_rows, long long first, long long count) {
   SearchState& s = h->search;
+  if (s.d.pos) {  // position-major rows are only ever scored in place, by their own kernel
+    if (!cur_rows) return fail(SB_ERR_STATE, "position-major populations have no proposal rows");
+    SearchFuse sf = {};
+    sf.cur_mk = s.d.cur_mk;
+    const bool reduced = (s.p.flags & SB_FLAG_REDUCED) != 0;
+    CK(search_pos_launch(h->dev, s.d, reduced ? h->tmin : h->tab, (reduced ? 1 : h->S) * kSlots, s.p.flags, first,
+                         count, true, sf, h->stream));
+    return SB_OK;
+  }
   EvalCall c;
   const uint8_t* ro = (cur_rows ? s.d.cur_o : s.d.prop_o) + first * s.d.stride_o;
   const uint8_t* rp = (cur_rows ? s.d.cur_p : s.d.prop_p) + first * s.d.stride_p;
@@ -596,9 +622,20 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   CK(cudaMemsetAsync(d.keys, 0xff, 2 * sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(d.cur_o, 0, P * d.stride_o, h->stream));
   CK(cudaMemsetAsync(d.cur_p, 0, P * d.stride_p, h->stream));
-  CK(search_init_population(d, h->stream));
+  // Rows that do not fit in shared memory: keep the population in schedule order and stream both rows.
+  const int SGs = (reduced ? 1 : h->S) * kSlots;
+  const bool no_fused = (p->flags & 0x20000000u) != 0;  // test hook
+  const int mode = search_round_mode(h->dev, J, SGs, h->nodes);
+  d.pos = (!no_fused && mode != 2 && search_pos_smem(J, SGs, h->nodes, 16) <= h->dev.smem_optin) ? 1 : 0;
+  if (d.pos) CK(search_init_population_pos(d, h->stream));
+  else CK(search_init_population(d, h->stream));
   s.ready = true;
+  std::vector<uint8_t> by_pos;
   if (warm_opt && warm_prio) {
+    if (d.pos) {
+      opt_to_positions(J, pb, warm_opt, warm_prio, &by_pos);
+      warm_opt = by_pos.data();
+    }
     CK(cudaMemsetAsync(s.cand_o, 0, d.stride_o, h->stream));
     CK(cudaMemsetAsync(s.cand_p, 0, d.stride_p, h->stream));
     CK(cudaMemcpyAsync(s.cand_o, warm_opt, J, cudaMemcpyHostToDevice, h->stream));
@@ -616,7 +653,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   s.scale = isfinite(mk) ? mk : 1.0f;
   s.evaluated = d.chains;
   s.rounds_done = 0;
-  s.fused_ok = !(p->flags & 0x20000000u) && (search_round_mode(h->dev, J, (reduced ? 1 : h->S) * kSlots, h->nodes) != 0);
+  s.fused_ok = d.pos || (!no_fused && mode != 0);
   return SB_OK;
 }
 
@@ -635,7 +672,18 @@ int sb_search_round(sb_handle* h, int rounds) {
     else tf = s.p.t_start * powf(s.p.t_end / s.p.t_start, frac);
     const float temperature = tf * s.scale;
     bool fused = false;
-    if (s.fused_ok) {
+    if (s.d.pos) {
+      SearchFuse sf;
+      sf.cur_mk = s.d.cur_mk; sf.cur_o = s.d.cur_o; sf.cur_p = s.d.cur_p;
+      sf.vopt = s.d.vopt; sf.nvalid = s.d.nvalid;
+      sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
+      sf.temperature = temperature;
+      const bool reduced = (s.p.flags & SB_FLAG_REDUCED) != 0;
+      CK(search_pos_launch(h->dev, s.d, reduced ? h->tmin : h->tab, (reduced ? 1 : h->S) * kSlots, s.p.flags, 0,
+                           s.d.chains, false, sf, h->stream));
+      CK(search_keep_best(s.d, true, h->stream));
+      fused = true;
+    } else if (s.fused_ok) {
       EvalCall c;
       if ((rc = make_call(h, s.d.cur_o, s.d.cur_p, s.d.chains, s.d.stride_o, s.p.flags, &c))) return rc;
       c.best_key = s.d.keys;
@@ -685,6 +733,16 @@ int sb_search_best(sb_handle* h, uint8_t* opt, void* prio, float* makespan, uint
   if (opt) CK(cudaMemcpyAsync(opt, s.d.best_o, s.d.J, cudaMemcpyDeviceToHost, h->stream));
   if (prio) CK(cudaMemcpyAsync(prio, s.d.best_p, static_cast<size_t>(s.d.J) * s.d.pb, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (s.d.pos && opt) {
+    std::vector<uint8_t> pr(static_cast<size_t>(s.d.J) * s.d.pb);
+    if (prio) {
+      memcpy(pr.data(), prio, pr.size());
+    } else {
+      CK(cudaMemcpyAsync(pr.data(), s.d.best_p, pr.size(), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    opt_from_positions(s.d.J, s.d.pb, opt, pr.data());
+  }
   if (makespan) {
     uint32_t bits = static_cast<uint32_t>(keys[1] >> 32);
     memcpy(makespan, &bits, 4);
@@ -716,6 +774,11 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
   if (copies > s.d.chains) copies = static_cast<int>(s.d.chains);
   long long first = first_chain < 0 ? s.d.chains - copies : first_chain;
   if (first + copies > s.d.chains) first = s.d.chains - copies;
+  std::vector<uint8_t> by_pos;
+  if (s.d.pos) {
+    opt_to_positions(s.d.J, s.d.pb, opt, prio, &by_pos);
+    opt = by_pos.data();
+  }
   CK(cudaMemsetAsync(s.cand_o, 0, s.d.stride_o, h->stream));
   CK(cudaMemsetAsync(s.cand_p, 0, s.d.stride_p, h->stream));
   CK(cudaMemcpyAsync(s.cand_o, opt, s.d.J, cudaMemcpyHostToDevice, h->stream));

@@ -25,7 +25,7 @@
 //     conflict-free); a step loads the state of the job's node, updates it, stores it back;
 //   * makespans are written coalesced (128 B per warp); an optional 64-bit arg-min key is
 //     folded with one redux + one atomicMin per warp.
-#include "sb_internal.h"
+#include "sb_lane.cuh"
 
 namespace sb {
 
@@ -49,244 +49,11 @@ struct TileArgs {
   XchgPost xp;    // xp.counter != nullptr: the last CTA to finish posts *best_key to every peer's mailbox
 };
 
-struct PrioChunk {
-  uint32_t w[8];  // 32 bytes = 32 (u8) or 16 (u16) schedule positions
-};
-// kReadOnly: the rows are not written during the kernel (evaluation) -> non-coherent path; the fused
-// search round writes accepted moves back into the same rows, so it uses the coherent form.
-template <bool kReadOnly>
-__device__ __forceinline__ PrioChunk ld_prio32(const uint8_t* p) {
-  PrioChunk c;
-  if (kReadOnly) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]),
-                   "=r"(c.w[7])
-                 : "l"(p));
-  } else {
-    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]),
-                   "=r"(c.w[7])
-                 : "l"(p)
-                 : "memory");
-  }
-  return c;
-}
-
-// Per-lane evaluation state + the per-job step.
-template <bool INT, bool MULTI>
-struct LaneState {
-  float f[8];
-  float mk;
-  const uint8_t* orow;  // this candidate's opt bytes (shared memory or global)
-  const float* tab;     // runtime table (shared memory or global)
-  int SG;
-  int one;
-  float4* ns;  // MULTI: lane-private node-state column; node n lives at ns[(2n)*32], ns[(2n+1)*32]
-  int cur;     // MULTI: the node whose state is currently in f[] (its shared-memory copy is stale)
-
-  __device__ __forceinline__ void reset(int nodes) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = 0.f;
-    mk = 0.f;
-    cur = 0;
-    if (MULTI) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int n = 0; n < 2 * nodes; ++n) ns[n * 32] = z;
-    }
-  }
-  // MULTI: bring node n's sorted state into the registers (write the previous node's back first).
-  // Lanes whose job stays on the same node as their previous job skip the shared-memory round trip.
-  __device__ __forceinline__ void switch_node(int n) {
-    if (n != cur) {
-      float4* old = ns + (2 * cur) * 32;
-      old[0] = make_float4(f[0], f[1], f[2], f[3]);
-      old[32] = make_float4(f[4], f[5], f[6], f[7]);
-      const float4* slot = ns + (2 * n) * 32;
-      const float4 lo = slot[0], hi = slot[32];
-      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
-      f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
-      cur = n;
-    }
-  }
-  // the two look-ups of a step (opt byte, then runtime) do not depend on the slot state, so callers
-  // that read from global memory resolve a batch of positions first (memory-level parallelism)
-  __device__ __forceinline__ int lookup_opt(int j) const { return orow[j]; }
-  __device__ __forceinline__ float lookup_rt(int j, int o) const {
-    return MULTI ? tab[j * 8 + (o & 7)] : tab[j * SG + o];
-  }
-  __device__ __forceinline__ void step_resolved(int o, float rt) {
-    if (!MULTI) {
-      ls_step<INT>(f, mk, rt, o & 7, one);
-    } else {
-      switch_node(o >> 3);
-      ls_step<INT, true>(f, mk, rt, o & 7, one);
-    }
-  }
-  __device__ __forceinline__ void step(int j) {
-    const int o = orow[j];
-    if (!MULTI) {
-      const float rt = tab[j * SG + o];
-      ls_step<INT>(f, mk, rt, o & 7, one);
-    } else {
-      const int col = o & 7;  // reduced table only: opt = (node << 3) | (k - 1)
-      const float rt = tab[j * 8 + col];
-      switch_node(o >> 3);
-      ls_step<INT, true>(f, mk, rt, col, one);
-    }
-  }
-  __device__ __forceinline__ float result() const { return (INT || MULTI) ? mk : f[7]; }
-};
-
-template <int PB>
-__device__ __forceinline__ int prio_at(const uint32_t* w, int t) {
-  // one PRMT per position: pick byte(s) t of the word, zero the rest (selector nibble 4 = byte 0 of
-  // the second operand, which is 0)
-  if (PB == 1) return static_cast<int>(__byte_perm(w[t >> 2], 0u, 0x4440u + (t & 3)));
-  return static_cast<int>(__byte_perm(w[t >> 1], 0u, (t & 1) ? 0x4432u : 0x4410u));
-}
-
-__device__ __forceinline__ void fold_best(unsigned long long* best_key, bool active, float mk, uint32_t id, int lane) {
-  const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
-  const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-  const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
-  if (lane == __ffs(who) - 1 && active) {
-    const unsigned long long key = pack_key(mk, id);
-    if (key < *reinterpret_cast<volatile unsigned long long*>(best_key)) atomicMin(best_key, key);
-  }
-}
-
-// ---- SEARCH variant: one Metropolis round fused into the tile kernel.  The rows a warp fetched
-// are the chains' CURRENT candidates; every lane applies its own random move to its private
-// shared-memory rows, scores the result, decides acceptance and — only when accepted — writes the
-// few changed bytes back to the chain's rows in HBM.  No proposal buffer, no separate propose /
-// accept kernels (they cost 60 % of an unfused round at 1 M chains, profiles/r01_search_round.md).
-struct Move {
-  int kind;  // 0 none, 1 opt byte of job a changed, 2 positions a,b swapped, 3 positions [a..b] rewritten
-  int a, b;
-  int va, vb;  // kind 2 on streamed prio rows: the jobs that were at positions a and b
-};
-
-__device__ __forceinline__ uint32_t bounded32(uint64_t r, uint32_t n) {
-  return static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(r >> 32)) * n) >> 32);
-}
-
-template <int PB>
-__device__ __forceinline__ int smem_prio_ld(const uint8_t* row, int i) {
-  return PB == 1 ? row[i] : reinterpret_cast<const uint16_t*>(row)[i];
-}
-template <int PB>
-__device__ __forceinline__ void smem_prio_st(uint8_t* row, int i, int v) {
-  if (PB == 1) row[i] = static_cast<uint8_t>(v);
-  else reinterpret_cast<uint16_t*>(row)[i] = static_cast<uint16_t>(v);
-}
-
-// `prow` is the lane's prio row in SHARED memory (non-streaming variant: the move is applied in place) or,
-// with STREAMED = true, its row in GLOBAL memory (read-only here: a swap is applied on the fly to the
-// chunks as they stream through registers, see patch_chunk; re-insertion moves are not proposed).
-template <int PB, bool STREAMED>
-__device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t gid, uint8_t* orow, const uint8_t* prow_c) {
-  uint8_t* prow = const_cast<uint8_t*>(prow_c);
-  Move m;
-  m.kind = 0; m.a = 0; m.b = 0; m.va = 0; m.vb = 0;
-  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * sf.round + 0);
-  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * sf.round + 1);
-  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * sf.round + 2);
-  const uint32_t kind = bounded32(r0, 100);
-  if (sf.nodes > 1 && kind >= 85) {  // move one job to another node (milp.py:117-137)
-    const int j = bounded32(r1, J);
-    const uint8_t curv = orow[j];
-    int nn = bounded32(r2, sf.nodes - 1);
-    if (nn >= (curv >> 3)) ++nn;
-    orow[j] = static_cast<uint8_t>((curv & 7) | (nn << 3));
-    m.kind = 1; m.a = j;
-    return m;
-  }
-  if (kind < 30) {  // change one job's option (keeping its node)
-    const int j = bounded32(r1, J);
-    const int n = sf.nvalid[j];
-    if (n > 1) {
-      const int pick = bounded32(r2, n - 1);
-      const uint8_t curv = orow[j];
-      const uint8_t node_bits = sf.nodes > 1 ? (curv & 0xf8) : 0;
-      const uint8_t cur_opt = sf.nodes > 1 ? (curv & 7) : curv;
-      uint8_t nv = sf.vopt[j * kSlots + pick];
-      if (nv == cur_opt) nv = sf.vopt[j * kSlots + n - 1];
-      orow[j] = nv | node_bits;
-      m.kind = 1; m.a = j;
-      return m;
-    }
-  }
-  if (J < 2) return m;
-  const int a = bounded32(r1, J);
-  if (STREAMED || kind < 70) {  // swap two priorities
-    int b = bounded32(r2, J - 1);
-    if (b >= a) ++b;
-    const int va = smem_prio_ld<PB>(prow, a), vb = smem_prio_ld<PB>(prow, b);
-    if (!STREAMED) {
-      smem_prio_st<PB>(prow, a, vb);
-      smem_prio_st<PB>(prow, b, va);
-    }
-    m.kind = 2; m.a = a; m.b = b; m.va = va; m.vb = vb;
-    return m;
-  }
-  // re-insert the job at position a up to 48 places earlier or later
-  const int span = J - 1 < 48 ? J - 1 : 48;
-  int d = 1 + static_cast<int>(bounded32(r2, 2 * span));  // 1..2*span
-  int b = d <= span ? a + d : a - (d - span);
-  if (b < 0) b = 0;
-  if (b > J - 1) b = J - 1;
-  if (b == a) return m;
-  const int va = smem_prio_ld<PB>(prow, a);
-  if (a < b) {
-    for (int i = a; i < b; ++i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i + 1));
-  } else {
-    for (int i = a; i > b; --i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i - 1));
-  }
-  smem_prio_st<PB>(prow, b, va);
-  m.kind = 3; m.a = a < b ? a : b; m.b = a < b ? b : a;
-  return m;
-}
-
-template <int PB>
-__device__ __forceinline__ void write_back(const Move& m, const uint8_t* orow, const uint8_t* prow, uint8_t* go,
-                                           uint8_t* gp) {
-  if (m.kind == 1) {
-    go[m.a] = orow[m.a];
-  } else if (m.kind == 2) {
-    // positions a and b exchange their jobs (values carried in the move: valid for both variants)
-    if (PB == 1) { gp[m.a] = static_cast<uint8_t>(m.vb); gp[m.b] = static_cast<uint8_t>(m.va); }
-    else {
-      reinterpret_cast<uint16_t*>(gp)[m.a] = static_cast<uint16_t>(m.vb);
-      reinterpret_cast<uint16_t*>(gp)[m.b] = static_cast<uint16_t>(m.va);
-    }
-  } else if (m.kind == 3) {
-    for (int i = m.a; i <= m.b; ++i) {
-      if (PB == 1) gp[i] = prow[i];
-      else reinterpret_cast<uint16_t*>(gp)[i] = reinterpret_cast<const uint16_t*>(prow)[i];
-    }
-  }
-}
-
-// Streamed prio rows: overwrite schedule position `pos` with job `val` in the 256-bit chunk `c` held in
-// registers (no dynamic register indexing: the word is selected by predication over the 8 words).
-template <int PB>
-__device__ __forceinline__ void patch_chunk(PrioChunk& q, int c, int pos, int val) {
-  constexpr int STEPS = 32 / PB;
-  if (pos / STEPS != c) return;
-  const int t = pos % STEPS;
-  const int widx = PB == 1 ? (t >> 2) : (t >> 1);
-  const int sh = PB == 1 ? (t & 3) * 8 : (t & 1) * 16;
-  const uint32_t mask = (PB == 1 ? 0xffu : 0xffffu) << sh;
-  const uint32_t ins = static_cast<uint32_t>(val) << sh;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i == widx) q.w[i] = (q.w[i] & ~mask) | ins;
-}
-
 // TABG: the runtime table stays in global memory (read through L1/L2) — for tables larger than the
 // shared memory left beside the opt tiles (e.g. J = 1024 with 8 strategies: 256 KB).
 template <int PB, bool INT, bool STREAM, bool MULTI, bool SEARCH = false, bool TABG = false>
 __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const TileArgs a) {
+  static_assert(!(SEARCH && (STREAM || TABG)), "the fused search round runs on shared-memory tiles only");
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -380,7 +147,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + (b0 + lane) * a.stride_o, a.copy_o, bar_w);
         if (!STREAM) tma_bulk_g2s(tile_p + lane * a.row_p, pg, a.copy_p, bar_w);
       }
-      if (STREAM && active) q = ld_prio32<!SEARCH>(pg);  // overlaps the TMA wait
+      if (STREAM && active) q = ld_prio32<true>(pg);  // overlaps the TMA wait
       mbar_wait(bar_w, phase);
       phase ^= 1;
     } else {
@@ -401,8 +168,8 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     Move mv;
     mv.kind = 0; mv.a = 0; mv.b = 0;
     if (SEARCH && active)
-      mv = apply_move<PB, STREAM>(a.sf, a.J, a.sf.chain_base + static_cast<uint64_t>(b0 + lane),
-                                  tile_o + lane * a.row_o, STREAM ? pg : tile_p + lane * a.row_p);
+      mv = apply_move<PB>(a.sf, a.J, a.sf.chain_base + static_cast<uint64_t>(b0 + lane), tile_o + lane * a.row_o,
+                          tile_p + lane * a.row_p);
     if (active) {
       st.reset(a.nodes);
       const int J = a.J;
@@ -411,11 +178,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         const int nch = (J + STEPS - 1) / STEPS;
         for (int c = 0; c < nch; ++c) {
           PrioChunk nxt = q;
-          if (c + 1 < nch) nxt = ld_prio32<!SEARCH>(pg + (c + 1) * 32);
-          if (SEARCH && mv.kind == 2) {  // the proposed swap, applied to the stream
-            patch_chunk<PB>(q, c, mv.a, mv.vb);
-            patch_chunk<PB>(q, c, mv.b, mv.va);
-          }
+          if (c + 1 < nch) nxt = ld_prio32<true>(pg + (c + 1) * 32);
           if ((c + 1) * STEPS <= J) {
 #pragma unroll
             for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(q.w, t));
@@ -785,7 +548,7 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
 // cudaErrorNotSupported when the shared-memory tiles (both rows resident, >= 4 warps) do not fit;
 // the caller then runs the unfused propose / evaluate / accept round.
 template <int PB, bool INT>
-static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const TilePlan& tp, bool multi, bool stream,
+static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const TilePlan& tp, bool multi,
                                    cudaStream_t st) {
   auto launch = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem));
@@ -795,22 +558,17 @@ static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const T
     kern<<<grid, tp.warps * 32, tp.smem, st>>>(a);
     return cudaGetLastError();
   };
-  if (stream) {
-    if (multi) return launch(k_eval_tiles<PB, INT, true, true, true>);
-    return launch(k_eval_tiles<PB, INT, true, false, true>);
-  }
   if (multi) return launch(k_eval_tiles<PB, INT, false, true, true>);
   return launch(k_eval_tiles<PB, INT, false, false, true>);
 }
 
-// 2 = both rows resident (all moves), 1 = opt rows resident + prio streamed (large J: no re-insertion
-// moves), 0 = neither fits: unfused rounds
+// 2 = both rows of a candidate fit in shared memory for at least 4 warps: the tile kernel runs the fused
+// round (all moves); 0 = they do not: the search keeps a position-major population (sb_search.cu) or, when
+// even the table does not fit, runs unfused rounds
 int search_round_mode(const Device& dev, int J, int SG, int nodes) {
   const int pb = J <= 256 ? 1 : 2;
   TilePlan tp;
-  if (plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 4) return 2;
-  if (plan_tiles(dev, J, SG, pb, true, nodes, &tp) >= 2) return 1;
-  return 0;
+  return plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 4 ? 2 : 0;
 }
 
 cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st) {
@@ -820,12 +578,9 @@ cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const Sear
   const bool bulk_ok = (c.stride_o % 16 == 0) && (c.stride_p % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(c.opt) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.prio) % 16 == 0);
   TilePlan tp;
-  const int mode = search_round_mode(dev, c.J, c.SG, c.nodes);
-  const bool stream = mode == 1;
-  if (mode == 0 || !bulk_ok) return cudaErrorNotSupported;
-  plan_tiles(dev, c.J, c.SG, pb, stream, c.nodes, &tp);
-  if (c.stride_o < tp.copy_o || c.stride_p < (stream ? ((c.J * pb + 31) & ~31) : tp.copy_p)) return cudaErrorNotSupported;
-  if (stream && (c.stride_p % 32 != 0 || reinterpret_cast<uintptr_t>(c.prio) % 32 != 0)) return cudaErrorNotSupported;
+  if (search_round_mode(dev, c.J, c.SG, c.nodes) == 0 || !bulk_ok) return cudaErrorNotSupported;
+  plan_tiles(dev, c.J, c.SG, pb, false, c.nodes, &tp);
+  if (c.stride_o < tp.copy_o || c.stride_p < tp.copy_p) return cudaErrorNotSupported;
   TileArgs a;
   a.tab = c.tab; a.J = c.J; a.SG = c.SG; a.opt = c.opt; a.prio = c.prio; a.B = c.B;
   a.stride_o = c.stride_o; a.stride_p = c.stride_p;
@@ -837,10 +592,10 @@ cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const Sear
   a.one = 1;
   a.sf = sf;
   if (pb == 1)
-    return ints ? dispatch_search<1, true>(dev, a, tp, c.nodes > 1, stream, st)
-                : dispatch_search<1, false>(dev, a, tp, c.nodes > 1, stream, st);
-  return ints ? dispatch_search<2, true>(dev, a, tp, c.nodes > 1, stream, st)
-              : dispatch_search<2, false>(dev, a, tp, c.nodes > 1, stream, st);
+    return ints ? dispatch_search<1, true>(dev, a, tp, c.nodes > 1, st)
+                : dispatch_search<1, false>(dev, a, tp, c.nodes > 1, st);
+  return ints ? dispatch_search<2, true>(dev, a, tp, c.nodes > 1, st)
+              : dispatch_search<2, false>(dev, a, tp, c.nodes > 1, st);
 }
 
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st) {

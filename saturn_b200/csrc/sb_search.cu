@@ -12,6 +12,7 @@
 // Random numbers are counter-based (seed, global chain id, round), so a run is reproducible and
 // independent of how chains are sharded across GPUs.
 #include "sb_search.h"
+#include "sb_lane.cuh"
 
 namespace sb {
 
@@ -190,6 +191,222 @@ __global__ void k_resample(SearchDev s, int round) {
   if (lane == 0) s.prop_mk[c] = s.cur_mk[src];
 }
 
+// =====================================================================================================
+// Large J: schedule-order ("position-major") populations.
+//
+// When a candidate's two rows no longer fit in shared memory (J beyond ~450 with u16 priorities) the
+// search keeps its population with opt stored BY POSITION — opt[i] is the option of the job scheduled
+// i-th, prio[i] that job — so a candidate is simply a sequence of (job, option) pairs.  Both rows are
+// then consumed in order: they stream through registers with 256-bit loads, no shared-memory tile is
+// needed (16 warps per SM at any J) and a move is a patch of one or two positions of the streams.
+// The encoding is internal to the search: candidates enter (warm start, injected seeds) and leave
+// (sb_search_best) in the job-indexed encoding of the ABI; sb_api.cu converts on the host.
+// =====================================================================================================
+template <int PB>
+__global__ void k_init_population_pos(SearchDev s) {
+  const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= s.chains) return;
+  uint8_t* orow = s.cur_o + c * s.stride_o;
+  uint8_t* prow = s.cur_p + c * s.stride_p;
+  const uint64_t gid = s.chain_base + static_cast<uint64_t>(c);
+  for (int j = 0; j < s.J; ++j) prio_st<PB>(prow, j, j);
+  for (int i = s.J - 1; i > 0; --i) {
+    const uint64_t r = rng_u64(s.seed, gid, 0x200000000ull + i);
+    const int k = bounded(r, i + 1);
+    const int a = prio_ld<PB>(prow, i), b = prio_ld<PB>(prow, k);
+    prio_st<PB>(prow, i, b);
+    prio_st<PB>(prow, k, a);
+  }
+  for (int i = 0; i < s.J; ++i) {
+    const int j = prio_ld<PB>(prow, i);
+    const uint64_t r = rng_u64(s.seed, gid, 0x100000000ull + j);
+    uint8_t ob = s.vopt[j * kSlots + bounded(r, s.nvalid[j])];
+    if (s.nodes > 1) ob = static_cast<uint8_t>((ob & 7) | (bounded(rng_u64(s.seed, gid, 0x300000000ull + j), s.nodes) << 3));
+    orow[i] = ob;
+  }
+}
+
+struct PosArgs {
+  const float* tab;
+  int J, SG, nodes;
+  uint8_t* opt;   // [chains][stride_o], by position
+  uint8_t* prio;  // [chains][stride_p]
+  long long chains, first;
+  long long stride_o, stride_p;
+  unsigned long long* best_key;
+  uint32_t id_base;
+  int eval_only;  // 1: score the rows as they are and store cur_mk (initialisation, injected rows)
+  int one;
+  SearchFuse sf;
+};
+
+struct PosMove {
+  int kind;    // 0 none, 1 option byte at position a becomes oa, 2 positions a and b exchange (job, option)
+  int a, b;
+  int va, vb;  // jobs at a, b
+  int oa, ob;  // option bytes at a, b (kind 1: oa = the new byte)
+};
+
+template <int PB>
+__device__ __forceinline__ PosMove make_pos_move(const SearchFuse& sf, int J, uint64_t gid, const uint8_t* og,
+                                                 const uint8_t* pg) {
+  PosMove m;
+  m.kind = 0; m.a = m.b = m.va = m.vb = m.oa = m.ob = 0;
+  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * sf.round + 0);
+  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * sf.round + 1);
+  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * sf.round + 2);
+  const uint32_t kind = bounded(r0, 100);
+  if (sf.nodes > 1 && kind >= 85) {  // move the job at a random position to another node
+    const int p = bounded(r1, J);
+    const int cur = og[p];
+    int nn = bounded(r2, sf.nodes - 1);
+    if (nn >= (cur >> 3)) ++nn;
+    m.kind = 1; m.a = p; m.oa = (cur & 7) | (nn << 3);
+    return m;
+  }
+  if (kind < 30) {  // change the option of the job at a random position (keeping its node)
+    const int p = bounded(r1, J);
+    const int j = prio_ld<PB>(pg, p);
+    const int n = sf.nvalid[j];
+    if (n > 1) {
+      const int cur = og[p];
+      const int node_bits = sf.nodes > 1 ? (cur & 0xf8) : 0;
+      const int cur_opt = sf.nodes > 1 ? (cur & 7) : cur;
+      int nv = sf.vopt[j * kSlots + bounded(r2, n - 1)];
+      if (nv == cur_opt) nv = sf.vopt[j * kSlots + n - 1];
+      m.kind = 1; m.a = p; m.oa = nv | node_bits;
+      return m;
+    }
+  }
+  if (J < 2) return m;
+  const int a = bounded(r1, J);
+  int b = bounded(r2, J - 1);
+  if (b >= a) ++b;
+  m.kind = 2; m.a = a; m.b = b;
+  m.va = prio_ld<PB>(pg, a); m.vb = prio_ld<PB>(pg, b);
+  m.oa = og[a]; m.ob = og[b];
+  return m;
+}
+
+template <int PB, bool INT, bool MULTI>
+__global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tab_bytes = static_cast<uint32_t>(a.J) * a.SG * 4u;
+  float* tab_s = reinterpret_cast<float*>(smem);
+  uint64_t* bar_tab = reinterpret_cast<uint64_t*>(smem + ((tab_bytes + 15u) & ~15u));
+  const uint32_t node_bytes = MULTI ? static_cast<uint32_t>(a.nodes) * 1024u : 0u;
+  float4* node_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bar_tab) + 16 + static_cast<size_t>(warp) * node_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_tab, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_tab, tab_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab);
+    for (uint32_t off = 0; off < tab_bytes; off += 32768u) tma_bulk_g2s(smem + off, src + off, min(32768u, tab_bytes - off), bar_tab);
+  }
+  LaneState<INT, MULTI> st;
+  st.tab = tab_s;
+  st.SG = a.SG;
+  st.one = a.one;
+  st.orow = nullptr;
+  st.ns = node_s + lane;
+  mbar_wait(bar_tab, 0);
+
+  const int J = a.J;
+  constexpr int PCH = PB;  // prio chunks (256-bit loads) per 32 positions
+  const long long ntiles = (a.chains + 31) / 32;
+  for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < ntiles;
+       tile += static_cast<long long>(gridDim.x) * nw) {
+    const long long c = a.first + tile * 32 + lane;
+    const bool active = tile * 32 + lane < a.chains;
+    float mk = 0.f;
+    PosMove mv;
+    mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = mv.oa = mv.ob = 0;
+    if (active) {
+      uint8_t* og = a.opt + c * a.stride_o;
+      uint8_t* pg = a.prio + c * a.stride_p;
+      if (!a.eval_only) mv = make_pos_move<PB>(a.sf, J, a.sf.chain_base + static_cast<uint64_t>(c), og, pg);
+      st.reset(a.nodes);
+      const int nout = (J + 31) / 32;  // outer iterations of 32 positions
+      PrioChunk qo = ld_prio32<false>(og);
+      PrioChunk qp[PCH];
+#pragma unroll
+      for (int h = 0; h < PCH; ++h) qp[h] = ld_prio32<false>(pg + h * 32);
+      for (int oc = 0; oc < nout; ++oc) {
+        PrioChunk no = qo, np[PCH];
+#pragma unroll
+        for (int h = 0; h < PCH; ++h) np[h] = qp[h];
+        if (oc + 1 < nout) {
+          no = ld_prio32<false>(og + (oc + 1) * 32);
+#pragma unroll
+          for (int h = 0; h < PCH; ++h)
+            if (((oc + 1) * PCH + h) * (32 / PB) < J) np[h] = ld_prio32<false>(pg + ((oc + 1) * PCH + h) * 32);
+        }
+        if (mv.kind == 1) {
+          patch_chunk<1>(qo, oc, mv.a, mv.oa);
+        } else if (mv.kind == 2) {
+          patch_chunk<1>(qo, oc, mv.a, mv.ob);
+          patch_chunk<1>(qo, oc, mv.b, mv.oa);
+#pragma unroll
+          for (int h = 0; h < PCH; ++h) {
+            patch_chunk<PB>(qp[h], oc * PCH + h, mv.a, mv.vb);
+            patch_chunk<PB>(qp[h], oc * PCH + h, mv.b, mv.va);
+          }
+        }
+        const int base = oc * 32;
+        if (base + 32 <= J) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const int j = prio_at<PB>(qp[(t * PB) / 32].w, t % (32 / PB));
+            const int o = prio_at<1>(qo.w, t);
+            st.step_resolved(o, st.lookup_rt(j, o));
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            if (base + t < J) {
+              const int j = prio_at<PB>(qp[(t * PB) / 32].w, t % (32 / PB));
+              const int o = prio_at<1>(qo.w, t);
+              st.step_resolved(o, st.lookup_rt(j, o));
+            }
+          }
+        }
+        qo = no;
+#pragma unroll
+        for (int h = 0; h < PCH; ++h) qp[h] = np[h];
+      }
+      mk = st.result();
+      if (a.eval_only) {
+        a.sf.cur_mk[c] = mk;
+      } else {
+        const float cm = a.sf.cur_mk[c];
+        bool acc = mk <= cm;
+        if (!acc && a.sf.temperature > 0.f && isfinite(mk)) {
+          const uint64_t r = rng_u64(a.sf.seed, a.sf.chain_base + static_cast<uint64_t>(c), 4ull * a.sf.round + 3);
+          const float u = (static_cast<uint32_t>(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
+          acc = u < __expf(-(mk - cm) / a.sf.temperature);
+        }
+        if (acc && mv.kind != 0) {
+          if (mv.kind == 1) {
+            og[mv.a] = static_cast<uint8_t>(mv.oa);
+          } else {
+            og[mv.a] = static_cast<uint8_t>(mv.ob);
+            og[mv.b] = static_cast<uint8_t>(mv.oa);
+            prio_st<PB>(pg, mv.a, mv.vb);
+            prio_st<PB>(pg, mv.b, mv.va);
+          }
+          a.sf.cur_mk[c] = mk;
+        }
+      }
+    }
+    if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static int warp_grid(long long warps, int threads) {
   long long blocks = (warps * 32 + threads - 1) / threads;
@@ -235,6 +452,56 @@ cudaError_t search_inject(const SearchDev& s, const uint8_t* cand_o, const uint8
   const int threads = 256;
   k_inject<<<warp_grid(copies, threads), threads, 0, st>>>(s, cand_o, cand_p, first, copies);
   return cudaGetLastError();
+}
+
+cudaError_t search_init_population_pos(const SearchDev& s, cudaStream_t st) {
+  const int threads = 128;
+  const int grid = static_cast<int>((s.chains + threads - 1) / threads);
+  if (s.pb == 1) k_init_population_pos<1><<<grid, threads, 0, st>>>(s);
+  else k_init_population_pos<2><<<grid, threads, 0, st>>>(s);
+  return cudaGetLastError();
+}
+
+// smem: table + mbarrier + per-warp node states (MULTI)
+size_t search_pos_smem(int J, int SG, int nodes, int warps) {
+  const size_t tab_bytes = (static_cast<size_t>(J) * SG * 4 + 15) & ~size_t(15);
+  return tab_bytes + 16 + static_cast<size_t>(warps) * (nodes > 1 ? nodes * 1024u : 0u);
+}
+
+cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float* tab, int SG, unsigned flags,
+                              long long first, long long count, bool eval_only, const SearchFuse& sf,
+                              cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  PosArgs a;
+  a.tab = tab; a.J = s.J; a.SG = SG; a.nodes = s.nodes;
+  a.opt = s.cur_o; a.prio = s.cur_p;
+  a.chains = count; a.first = first;
+  a.stride_o = s.stride_o; a.stride_p = s.stride_p;
+  a.best_key = s.keys;
+  a.id_base = static_cast<uint32_t>(s.chain_base + static_cast<uint64_t>(first));
+  a.eval_only = eval_only ? 1 : 0;
+  a.one = 1;
+  a.sf = sf;
+  const int warps = 16;
+  const size_t smem = search_pos_smem(s.J, SG, s.nodes, warps);
+  if (smem > dev.smem_optin) return cudaErrorNotSupported;
+  const bool ints = (flags & SB_FLAG_INTEGER_STARTS) != 0;
+  const bool multi = s.nodes > 1;
+  const long long ntiles = (count + 31) / 32;
+  const long long ctas = (ntiles + warps - 1) / warps;
+  const int grid = static_cast<int>(ctas < dev.sm_count ? ctas : dev.sm_count);
+  auto launch = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<grid, warps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+  };
+  if (s.pb == 1) {
+    if (multi) return ints ? launch(k_search_pos<1, true, true>) : launch(k_search_pos<1, false, true>);
+    return ints ? launch(k_search_pos<1, true, false>) : launch(k_search_pos<1, false, false>);
+  }
+  if (multi) return ints ? launch(k_search_pos<2, true, true>) : launch(k_search_pos<2, false, true>);
+  return ints ? launch(k_search_pos<2, true, false>) : launch(k_search_pos<2, false, false>);
 }
 
 }  // namespace sb

@@ -169,6 +169,47 @@ def test_fused_and_unfused_search_rounds(engine, J, S, nodes):
     assert abs(res[True] / res[False] - 1) < (0.02 if J <= 400 else 0.05)
 
 
+@pytest.mark.parametrize("J,nodes", [(1024, 1), (700, 2), (2048, 1), (513, 1)])
+def test_large_J_population_round_trips_candidates(engine, J, nodes):
+    """Large J: the search keeps its population in schedule order internally.  Candidates that enter (warm
+    start, injected rows) and the incumbent that leaves are in the ABI's job-indexed encoding: a
+    single-chain population returns exactly the warm candidate with the oracle's makespan, an injected
+    better candidate replaces it, and greedy rounds never lose the incumbent."""
+    T, _ = R.synth_table(J, 1, 8, seed=11, masked=False)
+    engine.set_table(T, nodes=nodes)
+    tab = R.reduce_table(R.canon_table(T, range(1, 9)))[0][:, None, :]
+    rng = np.random.default_rng(J)
+    def cand():
+        k = rng.integers(0, 8, size=J)
+        k = np.array([kk if np.isfinite(tab[j, 0, kk]) else int(np.argmin(tab[j, 0])) for j, kk in enumerate(k)])
+        o = (k | (rng.integers(0, nodes, size=J) << 3)).astype(np.uint8)
+        return o, rng.permutation(J).astype(np.uint16)
+    o1, p1 = cand()
+    mk1 = R.list_schedule(tab, o1, p1, True, np.float32, nodes=nodes)[0]
+    engine.search_init(1, seed=1, reduced=True, t_start=0.0, t_end=0.0, warm=(o1, p1))
+    assert engine.search_is_fused()
+    bo, bp, bm, _ = engine.search_best()
+    assert bm == mk1 and np.array_equal(bo, o1) and np.array_equal(bp, p1)
+    # a clearly better candidate (every job on its fastest option, spread over the nodes) takes over
+    o2 = (np.argmin(tab[:, 0, :], axis=1) | ((np.arange(J) % nodes) << 3)).astype(np.uint8)
+    p2 = np.argsort(-tab[np.arange(J), 0, o2 & 7], kind="stable").astype(np.uint16)
+    mk2 = R.list_schedule(tab, o2, p2, True, np.float32, nodes=nodes)[0]
+    engine.search_init(64, seed=2, reduced=True, t_start=0.0, t_end=0.0, warm=(o1, p1))
+    engine.search_inject(o2, p2, copies=8)
+    bo, bp, bm, _ = engine.search_best()
+    want = min(mk2, bm)
+    assert bm <= mk2
+    if bm == mk2:
+        assert np.array_equal(bo, o2) and np.array_equal(bp, p2)
+    engine.search_round(30)
+    engine.search_resample()
+    engine.search_round(30)
+    bo, bp, bm3, _ = engine.search_best()
+    assert bm3 <= want
+    assert sorted(bp.tolist()) == list(range(J))
+    assert R.list_schedule(tab, bo, bp, True, np.float32, nodes=nodes)[0] == bm3
+
+
 @pytest.mark.parametrize("J,chains", [(1, 1), (2, 5), (3, 33), (7, 64)])
 def test_tiny_problems_and_populations(J, chains):
     """Degenerate sizes: one task, populations smaller than a warp — the plan is still feasible and,
