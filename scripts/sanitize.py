@@ -22,4 +22,13 @@ for (J, S, G, B) in [(64, 6, 8, 2000), (100, 3, 8, 777), (300, 2, 8, 500)]:
     assert eng.validate(opt, prio) == 0
     r = run_search(eng, chains=2048, rounds=6, use_dist=False)
     eng.decode(r.opt, r.prio)
+# large J: position-major search populations (k_search_pos), ragged tails, one and two nodes
+for (J, nodes, chains) in [(1030, 1, 300), (777, 2, 130), (513, 1, 64)]:
+    T, valid = synth_table(J, 1, 8, seed=3)
+    eng.set_table(T, nodes=nodes)
+    r = run_search(eng, chains=chains, rounds=6, reduced=True, use_dist=False)
+    eng.search_inject(r.opt, r.prio, copies=3)
+    eng.search_resample()
+    eng.search_round(2)
+    eng.search_best()
 print("sanitize run ok")
