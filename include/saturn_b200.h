@@ -202,9 +202,10 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
 int sb_search_resample(sb_handle* h);
 /* 1 if rounds run as ONE fused kernel (move + evaluate + accept), 0 if they run as propose / evaluate /
  * accept kernels.  Fused rounds keep both rows of a tile's 32 candidates in shared memory when they fit
- * (all moves); for larger J only the opt rows are resident and the prio rows stream through registers,
- * with swaps applied to the stream on the fly (no re-insertion moves).  All forms are the same
- * Metropolis search; move mixes and RNG streams differ slightly. */
+ * (all moves); for larger J the population is held in schedule order (opt by position) and both rows
+ * stream through registers, with the move patched into the stream on the fly (no re-insertion moves).
+ * That layout is internal: every function of this header takes and returns job-indexed opt rows.  All
+ * forms are the same Metropolis search; move mixes and RNG streams differ slightly. */
 int sb_search_is_fused(sb_handle* h);
 /* candidates evaluated so far by this handle's searches */
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);
