@@ -111,10 +111,20 @@ __device__ __forceinline__ float psel(float a, float b, int bit) {
   return r;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // one FMNMX3
+  return d;
+}
+
 // kTrackMk: fold this job's completion (s + rt) into mk.  Needed with integer starts (the slot
 // state holds s + ceil(rt), not the completion) and with several nodes (no single f[7] at the end).
+// `ph` pairs the completions of two consecutive steps into one 3-input max: 0 parks this step's
+// completion in `pend`, 1 folds max(mk, pend, completion); callers with unrolled loops pass t & 1 (a
+// compile-time constant after unrolling), others pass -1 for the plain 2-input max.  A parked value
+// that is never folded is picked up by the final max(mk, pend) (LaneState::result).
 template <bool kIntegerStarts, bool kTrackMk = kIntegerStarts>
-__device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int km1, int one) {
+__device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float& pend, float rt, int km1, int one, int ph) {
   const float INF = inf_f();
   const int b2 = km1 & 4, b1 = km1 & 2, b0 = km1 & 1;
   // stage "shift by 4"
@@ -132,10 +142,14 @@ __device__ __forceinline__ void ls_step(float (&f)[8], float& mk, float rt, int 
   if (kIntegerStarts) {
     // every entry of f is an integer here, so s is; the slot is usable again at s + ceil(rt)
     v = s + ceilf(rt);
-    if (kTrackMk) mk = fmaxf(mk, s + rt);
   } else {
     v = s + rt;
-    if (kTrackMk) mk = fmaxf(mk, v);
+  }
+  if (kTrackMk) {
+    const float e = kIntegerStarts ? s + rt : v;
+    if (ph < 0) mk = fmaxf(mk, e);
+    else if (ph == 0) pend = e;
+    else mk = fmax3(mk, pend, e);
   }
   f[0] = fmaxf(f[0], fminf(v, x1));
   f[1] = fmaxf(f[1], fminf(v, x2));

@@ -181,12 +181,12 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
           if (c + 1 < nch) nxt = ld_prio32<true>(pg + (c + 1) * 32);
           if ((c + 1) * STEPS <= J) {
 #pragma unroll
-            for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(q.w, t));
+            for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(q.w, t), t & 1);
           } else {
             const int rem = J - c * STEPS;
 #pragma unroll
             for (int t = 0; t < STEPS; ++t)
-              if (t < rem) st.step(prio_at<PB>(q.w, t));
+              if (t < rem) st.step(prio_at<PB>(q.w, t), t & 1);
           }
           q = nxt;
         }
@@ -199,12 +199,12 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
           const uint32_t w[4] = {p.x, p.y, p.z, p.w};
           if ((c + 1) * STEPS <= J) {
 #pragma unroll
-            for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(w, t));
+            for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(w, t), t & 1);
           } else {
             const int rem = J - c * STEPS;
 #pragma unroll
             for (int t = 0; t < STEPS; ++t)
-              if (t < rem) st.step(prio_at<PB>(w, t));
+              if (t < rem) st.step(prio_at<PB>(w, t), t & 1);
           }
         }
       }
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(128) k_eval_generic(const GenericArgs a) {
 #pragma unroll
         for (int t = 0; t < BATCH; ++t) rts[t] = st.lookup_rt(js[t], os[t]);
 #pragma unroll
-        for (int t = 0; t < BATCH; ++t) st.step_resolved(os[t], rts[t]);
+        for (int t = 0; t < BATCH; ++t) st.step_resolved(os[t], rts[t], t & 1);
       }
       for (; i < a.J; ++i) st.step(PB == 1 ? prow[i] : reinterpret_cast<const uint16_t*>(prow)[i]);
       mk = st.result();

@@ -33,6 +33,7 @@ template <bool INT, bool MULTI>
 struct LaneState {
   float f[8];
   float mk;
+  float pend;  // a completion time parked by an even step (see ls_step)
   const uint8_t* orow;  // this candidate's opt bytes (shared memory or global)
   const float* tab;     // runtime table (shared memory or global)
   int SG;
@@ -44,6 +45,7 @@ struct LaneState {
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = 0.f;
     mk = 0.f;
+    pend = 0.f;
     cur = 0;
     if (MULTI) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -70,27 +72,28 @@ struct LaneState {
   __device__ __forceinline__ float lookup_rt(int j, int o) const {
     return MULTI ? tab[j * 8 + (o & 7)] : tab[j * SG + o];
   }
-  __device__ __forceinline__ void step_resolved(int o, float rt) {
+  // ph: t & 1 inside fully unrolled loops, -1 elsewhere (see ls_step)
+  __device__ __forceinline__ void step_resolved(int o, float rt, int ph = -1) {
     if (!MULTI) {
-      ls_step<INT>(f, mk, rt, o & 7, one);
+      ls_step<INT>(f, mk, pend, rt, o & 7, one, ph);
     } else {
       switch_node(o >> 3);
-      ls_step<INT, true>(f, mk, rt, o & 7, one);
+      ls_step<INT, true>(f, mk, pend, rt, o & 7, one, ph);
     }
   }
-  __device__ __forceinline__ void step(int j) {
+  __device__ __forceinline__ void step(int j, int ph = -1) {
     const int o = orow[j];
     if (!MULTI) {
       const float rt = tab[j * SG + o];
-      ls_step<INT>(f, mk, rt, o & 7, one);
+      ls_step<INT>(f, mk, pend, rt, o & 7, one, ph);
     } else {
       const int col = o & 7;  // reduced table only: opt = (node << 3) | (k - 1)
       const float rt = tab[j * 8 + col];
       switch_node(o >> 3);
-      ls_step<INT, true>(f, mk, rt, col, one);
+      ls_step<INT, true>(f, mk, pend, rt, col, one, ph);
     }
   }
-  __device__ __forceinline__ float result() const { return (INT || MULTI) ? mk : f[7]; }
+  __device__ __forceinline__ float result() const { return (INT || MULTI) ? fmaxf(mk, pend) : f[7]; }
 };
 
 template <int PB>

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
           for (int t = 0; t < 32; ++t) {
             const int j = prio_at<PB>(qp[(t * PB) / 32].w, t % (32 / PB));
             const int o = prio_at<1>(qo.w, t);
-            st.step_resolved(o, st.lookup_rt(j, o));
+            st.step_resolved(o, st.lookup_rt(j, o), t & 1);
           }
         } else {
 #pragma unroll
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
             if (base + t < J) {
               const int j = prio_at<PB>(qp[(t * PB) / 32].w, t % (32 / PB));
               const int o = prio_at<1>(qo.w, t);
-              st.step_resolved(o, st.lookup_rt(j, o));
+              st.step_resolved(o, st.lookup_rt(j, o), t & 1);
             }
           }
         }
