@@ -68,6 +68,10 @@ typedef enum sb_status {
 #define SB_FLAG_INTEGER_STARTS 1u /* MILP start variables are Integer, milp.py:142-143 */
 #define SB_FLAG_REDUCED 2u        /* opt bytes carry s = 0; the min-over-strategies table is used
                                      (PerformanceEvaluator.py:101-115) */
+#define SB_FLAG_OPT_BY_POSITION 4u /* sb_eval only: opt[b][i] is the option of the job scheduled i-th (= of job
+                                    * prio[b][i]) instead of the option of job i.  Both rows are then consumed in
+                                    * order and stream through registers: no shared-memory tile, full occupancy
+                                    * at any J.  Needs 32-byte aligned rows. */
 #define SB_FLAG_POST_KEY 8u       /* sb_eval: when the last candidate is scored, publish *best_key in this
                                      rank's peer-visible mailbox (see sb_xchg_*); the same kernel does both */
 #define SB_FLAG_FOLD_PREV 16u     /* with SB_FLAG_POST_KEY: the kernel's prologue first MINs into *best_key the keys
@@ -115,6 +119,7 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
             unsigned flags, float* makespan_out, uint64_t* best_key, uint32_t id_base);
 
 /* which kernel the last sb_eval / sb_eval_host on this handle used:
+ * 5 = position-major kernel (SB_FLAG_OPT_BY_POSITION): both rows streamed with 256-bit loads,
  * 4 = as 3 but with the runtime table read from global memory (it does not fit in shared memory),
  * 3 = tile kernel, opt rows by TMA bulk copy + prio rows streamed with 256-bit loads (rows 32-byte
  *     aligned: the fast path), 2 = tile kernel with TMA bulk copies of both rows (16-byte aligned),

@@ -8,6 +8,7 @@ SO_PATH = os.environ.get("SATURN_B200_LIB") or os.path.join(_HERE, "libsaturn_b2
 
 FLAG_INTEGER_STARTS = 1
 FLAG_REDUCED = 2
+FLAG_OPT_BY_POSITION = 4
 FLAG_POST_KEY = 8
 FLAG_FOLD_PREV = 16
 IPC_HANDLE_BYTES = 64

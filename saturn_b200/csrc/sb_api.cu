@@ -259,8 +259,10 @@ int sb_get_reduced(sb_handle* h, float* tmin, uint8_t* args) {
 }
 
 static int make_call(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64_t row_stride, unsigned flags,
-                     EvalCall* c) {
+                     EvalCall* c, bool by_position_ok = false) {
   if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
+  if ((flags & SB_FLAG_OPT_BY_POSITION) && !by_position_ok)
+    return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_OPT_BY_POSITION is accepted by sb_eval only");
   if (B < 0) return fail(SB_ERR_ARG, "B=%lld is negative", static_cast<long long>(B));
   if (B > 0 && (!opt || !prio)) return fail(SB_ERR_ARG, "opt / prio is null");
   if (row_stride < h->J) return fail(SB_ERR_ARG, "row_stride=%lld < J=%d", static_cast<long long>(row_stride), h->J);
@@ -288,12 +290,25 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
   int rc = use_device(h);
   if (rc) return rc;
   EvalCall c;
-  rc = make_call(h, opt, prio, B, row_stride, flags, &c);
+  rc = make_call(h, opt, prio, B, row_stride, flags, &c, true);
   if (rc) return rc;
   if (B > 0 && !makespan_out) return fail(SB_ERR_ARG, "makespan_out is null");
   c.out = makespan_out;
   c.best_key = reinterpret_cast<unsigned long long*>(best_key);
   c.id_base = id_base;
+  if (flags & SB_FLAG_OPT_BY_POSITION) {
+    if (flags & (SB_FLAG_POST_KEY | SB_FLAG_FOLD_PREV))
+      return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_OPT_BY_POSITION cannot be combined with the fused key exchange");
+    cudaError_t e = eval_pos_launch(h->dev, c, h->stream);
+    if (e == cudaErrorNotSupported) {
+      cudaGetLastError();
+      return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_OPT_BY_POSITION needs 32-byte aligned rows (row_stride %% 32 == 0) and a "
+                  "table that fits in shared memory (J*S*32 bytes <= %zu)", h->dev.smem_optin - 16);
+    }
+    CK(e);
+    h->last_path = 5;
+    return SB_OK;
+  }
   c.force_generic = (flags & 0x80000000u) ? 1 : 0;  // test hooks: 0x80000000 generic kernel, 0x40000000 no streaming
   const bool post = (flags & SB_FLAG_POST_KEY) != 0;
   if (post) {

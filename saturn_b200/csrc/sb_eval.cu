@@ -18,7 +18,7 @@
 //     scheduler 31 % of issue slots were lost to dependency waits).  Unaligned rows fall back to
 //     the non-STREAM variant (prio rows staged in shared memory, TMA or plain loads);
 //   * one candidate per LANE: the 8 slot ready-times live sorted in 8 registers and one
-//     scheduling step is ~57 instructions (sb_common.cuh: ls_step) — fp32 min/max/add and byte
+//     scheduling step is ~51 instructions (sb_common.cuh: ls_step) — fp32 min/max/add and byte
 //     indexing only, no tensor cores;
 //   * MULTI variant (several nodes, milp.py:117-137: a gang stays inside one node): the sorted
 //     state of every node lives in a lane-private shared-memory column (2 x float4 per node,

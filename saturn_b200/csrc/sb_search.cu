@@ -504,4 +504,21 @@ cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float
   return ints ? launch(k_search_pos<2, true, false>) : launch(k_search_pos<2, false, false>);
 }
 
+// sb_eval with SB_FLAG_OPT_BY_POSITION: score caller rows whose opt bytes are in schedule order
+cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t st) {
+  if (c.B <= 0) return cudaSuccess;
+  if (c.stride_o % 32 != 0 || reinterpret_cast<uintptr_t>(c.opt) % 32 != 0 || reinterpret_cast<uintptr_t>(c.prio) % 32 != 0)
+    return cudaErrorNotSupported;
+  SearchDev s;
+  s.J = c.J; s.pb = c.J <= 256 ? 1 : 2; s.nodes = c.nodes;
+  s.cur_o = const_cast<uint8_t*>(c.opt);  // eval_only: rows are read, never written
+  s.cur_p = const_cast<uint8_t*>(c.prio);
+  s.chains = c.B; s.chain_base = c.id_base;
+  s.stride_o = c.stride_o; s.stride_p = c.stride_p;
+  s.keys = c.best_key;
+  SearchFuse sf = {};
+  sf.cur_mk = c.out;
+  return search_pos_launch(dev, s, c.tab, c.SG, c.flags, 0, c.B, true, sf, st);
+}
+
 }  // namespace sb

@@ -29,6 +29,7 @@ size_t search_pos_smem(int J, int SG, int nodes, int warps);
 cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float* tab, int SG, unsigned flags,
                               long long first, long long count, bool eval_only, const SearchFuse& sf,
                               cudaStream_t st);
+cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t st);
 cudaError_t search_resample(const SearchDev& s, int round, cudaStream_t st);
 cudaError_t search_inject(const SearchDev& s, const uint8_t* cand_o, const uint8_t* cand_p, long long first,
                           int copies, cudaStream_t st);

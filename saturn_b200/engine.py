@@ -122,14 +122,17 @@ class Engine:
 
     def eval(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False,
              out: Optional[torch.Tensor] = None, best_key: Optional[torch.Tensor] = None, id_base: int = 0,
-             _force_generic: bool = False, _no_stream: bool = False, post_key: bool = False, fold_prev: bool = False) -> torch.Tensor:
-        """Makespan of every candidate (device tensors).  Asynchronous on the handle's stream."""
+             _force_generic: bool = False, _no_stream: bool = False, post_key: bool = False, fold_prev: bool = False,
+             by_position: bool = False) -> torch.Tensor:
+        """Makespan of every candidate (device tensors).  Asynchronous on the handle's stream.
+        by_position: opt[b][i] is the option of the job scheduled i-th (see `opt_by_position`)."""
         B, stride = self._check_cands(opt, prio, True)
         if out is None:
             out = torch.empty(B, dtype=torch.float32, device=self.device)
         fl = _flags(integer_starts, reduced) | (_lib._FLAG_FORCE_GENERIC if _force_generic else 0) | (
             0x40000000 if _no_stream else 0) | (_lib.FLAG_POST_KEY if post_key else 0) | (
-            _lib.FLAG_FOLD_PREV if (post_key and fold_prev) else 0)
+            _lib.FLAG_FOLD_PREV if (post_key and fold_prev) else 0) | (
+            _lib.FLAG_OPT_BY_POSITION if by_position else 0)
         kp = C.c_void_p(best_key.data_ptr()) if best_key is not None else None
         check(self._lib.sb_eval(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride, fl,
                                 C.c_void_p(out.data_ptr()), kp, id_base & 0xffffffff))
@@ -291,6 +294,15 @@ def _alias_int64(ptr: int, device: torch.device) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------- candidate helpers
+def opt_by_position(opt: torch.Tensor, prio: torch.Tensor) -> torch.Tensor:
+    """Re-encode job-indexed opt rows in schedule order (opt'[b][i] = opt[b][prio[b][i]]), keeping the row
+    stride of `opt` — the encoding SB_FLAG_OPT_BY_POSITION evaluates."""
+    B, J = opt.shape
+    out = padded_rows(B, J, torch.uint8, opt.device)
+    out.copy_(torch.gather(opt, 1, prio.to(torch.int32).to(torch.int64)))
+    return out
+
+
 def padded_rows(B: int, J: int, dtype: torch.dtype, device, pinned: bool = False) -> torch.Tensor:
     """A [B][J] view into storage whose rows are a multiple of 32 ELEMENTS apart, so that the byte
     stride of both opt (u8) and prio (u8/u16) rows is 32-byte aligned (the kernel's fast path)."""

@@ -379,3 +379,47 @@ def test_error_paths_and_unpadded_host_buffers(engine):
         engine.eval(opt_h.to(engine.device).to(torch.int32), prio_h.to(engine.device))
     with pytest.raises(ValueError):
         engine.eval(opt_h.to(engine.device)[:, :50], prio_h.to(engine.device)[:, :50])
+
+
+@pytest.mark.parametrize("J,S,nodes,B", [(256, 8, 1, 3000), (64, 6, 1, 1500), (1024, 1, 1, 700), (700, 1, 2, 500),
+                                         (33, 2, 1, 77), (1500, 1, 1, 200)])
+@pytest.mark.parametrize("ints", [True, False])
+def test_opt_by_position_encoding(engine, J, S, nodes, B, ints):
+    """SB_FLAG_OPT_BY_POSITION: the same candidates with opt re-encoded in schedule order (kernel path 5:
+    both rows streamed through registers, no shared-memory tile) score bit-exactly like the oracle and like
+    the job-indexed rows, and fold the same arg-min key."""
+    from saturn_b200.engine import opt_by_position
+    T, valid = R.synth_table(J, S, 8, seed=J + S, masked=(S > 1))
+    engine.set_table(T, nodes=nodes)
+    reduced = S == 1
+    opt, prio = random_candidates(engine, B, valid, seed=5, nodes=nodes)
+    ref = c_oracle.evaluate(R.canon_table(T, range(1, 9)), opt.cpu().numpy(), prio.cpu().numpy(), ints, np.float32,
+                            threads=8, nodes=nodes)
+    key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=engine.device)
+    got = engine.eval(opt_by_position(opt, prio), prio, integer_starts=ints, reduced=reduced, by_position=True,
+                      best_key=key, id_base=1000)
+    assert engine.last_eval_path() == 5
+    assert np.array_equal(got.cpu().numpy(), ref)
+    assert torch.equal(got, engine.eval(opt, prio, integer_starts=ints, reduced=reduced))
+    i = int(np.argmin(ref))                                       # first index of the minimum
+    assert int(key.item()) == (int(ref[i:i + 1].view(np.uint32)[0]) << 32) | (1000 + i)
+
+
+def test_opt_by_position_is_refused_where_it_cannot_run(engine):
+    from saturn_b200.engine import opt_by_position
+    T, valid = R.synth_table(40, 2, 8, seed=1)
+    engine.set_table(T)
+    opt, prio = random_candidates(engine, 64, valid, seed=1)
+    with pytest.raises(RuntimeError, match="32-byte"):             # 40-byte rows
+        engine.eval(opt_by_position(opt, prio).contiguous(), prio.contiguous(), by_position=True)
+    with pytest.raises(RuntimeError, match="sb_eval only"):
+        from saturn_b200 import _lib
+        import ctypes as C
+        bad = C.c_int64(0)
+        _lib.check(engine._lib.sb_validate(engine._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), 64,
+                                           opt.stride(0), _lib.FLAG_OPT_BY_POSITION, C.byref(bad)))
+    T2, valid2 = R.synth_table(1024, 8, 8, seed=1)                 # 256 KB table: does not fit in shared memory
+    engine.set_table(T2)
+    o2, p2 = random_candidates(engine, 32, valid2, seed=1)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        engine.eval(opt_by_position(o2, p2), p2, by_position=True)
