@@ -336,10 +336,10 @@ def main():
         tmin_h = _np.where(valid, T, _np.inf).min(axis=1)
         tasks = [_Task("t%d" % j, {g + 1: Strategy("x", g + 1, {}, float(tmin_h[j, g])) for g in range(G)
                                     if _np.isfinite(tmin_h[j, g])}) for j in range(J)]
-        solve(tasks, None, engine=eng, chains=1 << 17, rounds=8)                  # warm-up
+        solve(tasks, None, engine=eng, rounds=8)                  # warm-up
         barrier()
         t0 = time.perf_counter()
-        plan = solve(tasks, None, engine=eng, chains=1 << 17, rounds=200)
+        plan = solve(tasks, None, engine=eng, rounds=200)
         dt = time.perf_counter() - t0
         stt = dict(sb_solver.last_stats)
         eng.set_table(T)                                                          # restore the bench table

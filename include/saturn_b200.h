@@ -205,6 +205,10 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
 /* tournament resampling: every chain continues from a random rival's candidate if the rival's
  * current makespan is strictly better (keeps the population concentrated on good basins) */
 int sb_search_resample(sb_handle* h);
+/* Population size that fills the device exactly once with the round kernel this table gets (resident warps
+ * per SM x 32 lanes x SMs).  A population that is a whole multiple of it leaves no partially filled last
+ * wave: 131,072 chains on 148 SMs x 12 warps are 2.3 waves and cost 3. */
+int sb_search_wave(sb_handle* h, unsigned flags, int64_t* chains);
 /* 1 if rounds run as ONE fused kernel (move + evaluate + accept), 0 if they run as propose / evaluate /
  * accept kernels.  Fused rounds keep both rows of a tile's 32 candidates in shared memory when they fit
  * (all moves); for larger J the population is held in schedule order (opt by position) and both rows

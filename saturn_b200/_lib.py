@@ -20,7 +20,7 @@ SYMBOLS = [
     "sb_set_sentinel", "sb_get_reduced", "sb_eval", "sb_last_eval_path", "sb_validate", "sb_eval_host", "sb_eval_full",
     "sb_decode", "sb_xchg_create", "sb_xchg_connect", "sb_xchg_post", "sb_xchg_reduce", "sb_xchg_check",
     "sb_search_init", "sb_search_round", "sb_search_best_key_ptr", "sb_search_best",
-    "sb_search_inject", "sb_search_resample", "sb_search_is_fused", "sb_search_stats",
+    "sb_search_inject", "sb_search_resample", "sb_search_wave", "sb_search_is_fused", "sb_search_stats",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
         "sb_search_best": [vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)],
         "sb_search_inject": [vp, vp, vp, i64, ci],
         "sb_search_resample": [vp],
+        "sb_search_wave": [vp, C.c_uint, C.POINTER(i64)],
         "sb_search_is_fused": [vp],
         "sb_search_stats": [vp, C.POINTER(i64), C.POINTER(i64)],
     }

@@ -806,6 +806,27 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
   return SB_OK;
 }
 
+int sb_search_wave(sb_handle* h, unsigned flags, int64_t* chains) {
+  if (!h || !chains) return fail(SB_ERR_ARG, "null argument");
+  if (h->J == 0) return fail(SB_ERR_STATE, "sb_set_table has not been called");
+  const bool reduced = (flags & SB_FLAG_REDUCED) != 0;
+  const int SG = (reduced ? 1 : h->S) * kSlots;
+  const int pb = h->J <= 256 ? 1 : 2;
+  int warps = 0;
+  TilePlan tp;
+  if (search_round_mode(h->dev, h->J, SG, h->nodes) == 2) {
+    plan_tiles(h->dev, h->J, SG, pb, false, h->nodes, &tp);
+    warps = tp.warps;
+  } else if (search_pos_smem(h->J, SG, h->nodes, 16) <= h->dev.smem_optin) {
+    warps = 16;
+  } else {  // unfused rounds: the evaluation kernel's own plan (1 warp stands for the generic kernel's 128-thread CTAs)
+    warps = plan_tiles(h->dev, h->J, SG, pb, true, h->nodes, &tp);
+    if (warps < 1) warps = 4;
+  }
+  *chains = static_cast<int64_t>(warps) * 32 * h->dev.sm_count;
+  return SB_OK;
+}
+
 int sb_search_is_fused(sb_handle* h) { return (h && h->search.ready && h->search.fused_ok) ? 1 : 0; }
 
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done) {

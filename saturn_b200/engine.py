@@ -242,6 +242,13 @@ class Engine:
         self._search_chains = chains
         self._search_base = chain_base
 
+    def search_wave(self, reduced: bool = False) -> int:
+        """Chains that fill the device exactly once with the round kernel of the current table; populations
+        that are whole multiples of it leave no partially filled last wave."""
+        n = C.c_int64(0)
+        check(self._lib.sb_search_wave(self._h, _flags(False, reduced), C.byref(n)))
+        return int(n.value)
+
     def search_is_fused(self) -> bool:
         return bool(self._lib.sb_search_is_fused(self._h))
 

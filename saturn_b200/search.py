@@ -77,12 +77,13 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
                target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 4,
                record_history: bool = False, heuristic_seeds: bool = True,
-               exchange_every: int = 4, _no_fused: bool = False) -> SearchResult:
+               exchange_every: int = 16, _no_fused: bool = False) -> SearchResult:
     """Run the search on `engine` (table already set).  Returns the best candidate found by any rank.
 
-    `rounds` device rounds are issued in groups of `exchange_every`; after each group the ranks
-    exchange their best key (one MIN all-reduce) and the stopping rules are evaluated, so the host
-    synchronises once per group rather than once per round."""
+    `rounds` device rounds are issued in groups of `exchange_every` (tournament resampling every
+    `resample_every` rounds inside a group is only another launch); after each group the ranks exchange
+    their best key (one MIN) and the stopping rules are evaluated, so the host synchronises once per
+    group rather than once per round."""
     dist = _dist() if use_dist else None
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
@@ -136,13 +137,19 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     if record_history:
         history.append((time.perf_counter() - t0, chains * world, key_makespan(key)))
     exchange_every = max(1, int(exchange_every))
-    if resample_every:
-        exchange_every = min(exchange_every, int(resample_every))
     while done_rounds < rounds:
+        # one group: `step` rounds with tournament resampling on its own cadence, no host synchronisation
         step = min(exchange_every, rounds - done_rounds)
-        if resample_every:                      # keep resampling on its own cadence
-            step = min(step, resample_every - (done_rounds % resample_every))
-        engine.search_round(step)
+        issued = 0
+        while issued < step:
+            n = step - issued
+            if resample_every:
+                n = min(n, resample_every - ((done_rounds + issued) % resample_every))
+            engine.search_round(n)
+            issued += n
+            at = done_rounds + issued
+            if resample_every and at % resample_every == 0 and at < rounds and issued < step:
+                engine.search_resample()
         done_rounds += step
         r = done_rounds - 1
         key = exchange()

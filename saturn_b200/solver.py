@@ -219,7 +219,11 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     nodes = int(nodes)
     eng.set_table(Tdev, list(range(1, NSLOT + 1)), sentinel=float("inf"), nodes=nodes)
     if chains is None:
-        chains = int(os.environ.get("SATURN_B200_CHAINS", 1 << 17))
+        chains = int(os.environ.get("SATURN_B200_CHAINS", 0))
+        if chains <= 0:
+            # about 131072 chains, rounded to whole waves of the round kernel (no partially filled last wave)
+            wave = eng.search_wave(reduced=True) if hasattr(eng, "search_wave") else 0
+            chains = max(1, round((1 << 17) / wave)) * wave if wave > 0 else 1 << 17
     if rounds is None:
         rounds = int(os.environ.get("SATURN_B200_ROUNDS", 400))
     budget = float(os.environ.get("SATURN_B200_BUDGET_S", 20.0))
