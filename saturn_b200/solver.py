@@ -62,9 +62,8 @@ def build_table(task_list):
     the table but never proposed unless a task has nothing else.
     """
     J = len(task_list)
-    T = np.full((J, 1, NSLOT), np.inf, dtype=np.float32)
-    optindex = np.full((J, NSLOT), -1, dtype=np.int64)
-    usable = np.zeros((J, NSLOT), dtype=bool)
+    # one pass over the Python objects collecting plain lists, the arithmetic is vectorised below
+    jj, kk, oo, rr, uu = [], [], [], [], []
     for j, task in enumerate(task_list):
         if len(task.strategies) == 0:
             raise SolverError("task %r has no strategies; run the trial runner first" % getattr(task, "name", j))
@@ -76,13 +75,30 @@ def build_table(task_list):
                 rt = 0.0        # forecast's in-place decrements (executor.py:166-168) can undershoot by an ulp
             if rt is None or not math.isfinite(rt) or rt < 0:
                 continue
-            v = _f32_ceil(float(rt))
-            if v < T[j, 0, g_count - 1]:
-                T[j, 0, g_count - 1] = v
-                optindex[j, g_count - 1] = o
-                usable[j, g_count - 1] = getattr(strat, "executor", True) is not None
-        if not np.isfinite(T[j]).any():
-            raise SolverError("task %r has no option that fits a node of %d GPUs" % (getattr(task, "name", j), NSLOT))
+            jj.append(j); kk.append(int(g_count) - 1); oo.append(o); rr.append(float(rt))
+            uu.append(getattr(strat, "executor", True) is not None)
+    T = np.full((J, 1, NSLOT), np.inf, dtype=np.float32)
+    optindex = np.full((J, NSLOT), -1, dtype=np.int64)
+    usable = np.zeros((J, NSLOT), dtype=bool)
+    if jj:
+        jj, kk, oo, uu = np.asarray(jj), np.asarray(kk), np.asarray(oo), np.asarray(uu)
+        r64 = np.asarray(rr, dtype=np.float64)
+        v = r64.astype(np.float32)                                   # smallest fp32 >= rt (see _f32_ceil)
+        low = v.astype(np.float64) < r64
+        v[low] = np.nextafter(v[low], np.float32(np.inf))
+        # dict keys are unique, so a (task, gpu_count) cell is written at most once; keep the first of the
+        # smallest anyway (e.g. the keys 2 and numpy.int64(2) of a hand-built dict)
+        order = np.lexsort((oo, v, kk, jj))
+        first = np.ones(len(order), dtype=bool)
+        first[1:] = (jj[order][1:] != jj[order][:-1]) | (kk[order][1:] != kk[order][:-1])
+        sel = order[first]
+        T[jj[sel], 0, kk[sel]] = v[sel]
+        optindex[jj[sel], kk[sel]] = oo[sel]
+        usable[jj[sel], kk[sel]] = uu[sel]
+    none = ~np.isfinite(T[:, 0, :]).any(axis=1)
+    if none.any():
+        j = int(np.argmax(none))
+        raise SolverError("task %r has no option that fits a node of %d GPUs" % (getattr(task_list[j], "name", j), NSLOT))
     return T, usable, optindex
 
 
