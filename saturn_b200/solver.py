@@ -44,14 +44,6 @@ def gpu_time_tuples_of(task_list) -> List[List[tuple]]:
     return out
 
 
-def _f32_ceil(x: float) -> np.float32:
-    """Smallest fp32 >= x, so that the device's (start + ceil(rt)) never under-estimates."""
-    v = np.float32(x)
-    if float(v) < x:
-        v = np.nextafter(v, np.float32(np.inf), dtype=np.float32)
-    return v
-
-
 def build_table(task_list):
     """Task.strategies -> (T[J][1][8] fp32 by gpu_count column, usable[J][8], optindex[J][8]).
 
@@ -83,7 +75,7 @@ def build_table(task_list):
     if jj:
         jj, kk, oo, uu = np.asarray(jj), np.asarray(kk), np.asarray(oo), np.asarray(uu)
         r64 = np.asarray(rr, dtype=np.float64)
-        v = r64.astype(np.float32)                                   # smallest fp32 >= rt (see _f32_ceil)
+        v = r64.astype(np.float32)                                   # smallest fp32 >= rt: the device's start + ceil(rt)
         low = v.astype(np.float64) < r64
         v[low] = np.nextafter(v[low], np.float32(np.inf))
         # dict keys are unique, so a (task, gpu_count) cell is written at most once; keep the first of the
