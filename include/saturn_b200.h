@@ -205,6 +205,40 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
 /* tournament resampling: every chain continues from a random rival's candidate if the rival's
  * current makespan is strictly better (keeps the population concentrated on good basins) */
 int sb_search_resample(sb_handle* h);
+/* ---- the whole single-GPU search in one call (what prob.solve(solver) is to the reference, milp.py:321-327)
+ * sb_search_seed_lpt plants three longest-processing-time candidates (every job on its fastest option / on its
+ * least GPU-seconds option / in between; nodes filled greedily by GPU-seconds) into an eighth of the
+ * population each and scores them.  sb_search_run = sb_search_init + seeds + `rounds` rounds in groups of
+ * `sync_every` (tournament resampling every `resample_every` rounds inside a group is only another launch;
+ * the host reads the incumbent key once per group and applies the stopping rules) + sb_search_best.
+ * The multi-GPU driver (saturn_b200/search.py) runs the same steps with a key exchange per group. */
+typedef struct sb_search_control {
+  int rounds;             /* >= 1 */
+  int resample_every;     /* 0 = never */
+  int sync_every;         /* rounds per group, >= 1 */
+  int patience;           /* stop after this many rounds without improvement; 0 = off */
+  int heuristic_seeds;    /* 1 = sb_search_seed_lpt after initialisation */
+  float target_makespan;  /* stop once the incumbent is <= this; <= 0 = off */
+  double time_budget_s;   /* wall-clock budget (the reference's timeLimit); <= 0 = none */
+  /* optional trace, one entry per group (NULL / 0 = none) */
+  int history_cap;
+  int* history_len;
+  double* history_wall_s;
+  int64_t* history_evaluated;
+  float* history_makespan;
+} sb_search_control;
+typedef struct sb_search_result {
+  float makespan;
+  uint64_t key;        /* (float bits << 32) | global chain id of the incumbent */
+  int64_t evaluated;   /* candidates scored */
+  int rounds;          /* rounds run */
+  int stop_reason;     /* 0 rounds exhausted, 1 time budget, 2 patience, 3 target reached */
+  double wall_s;
+} sb_search_result;
+int sb_search_seed_lpt(sb_handle* h);
+int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_control* c, const uint8_t* warm_opt,
+                  const void* warm_prio, uint8_t* opt_out /*host [J]*/, void* prio_out /*host [J]*/,
+                  sb_search_result* result);
 /* Population size that fills the device exactly once with the round kernel this table gets (resident warps
  * per SM x 32 lanes x SMs).  A population that is a whole multiple of it leaves no partially filled last
  * wave: 131,072 chains on 148 SMs x 12 warps are 2.3 waves and cost 3. */

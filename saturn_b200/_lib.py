@@ -20,7 +20,7 @@ SYMBOLS = [
     "sb_set_sentinel", "sb_get_reduced", "sb_eval", "sb_last_eval_path", "sb_validate", "sb_eval_host", "sb_eval_full",
     "sb_decode", "sb_xchg_create", "sb_xchg_connect", "sb_xchg_post", "sb_xchg_reduce", "sb_xchg_check",
     "sb_search_init", "sb_search_round", "sb_search_best_key_ptr", "sb_search_best",
-    "sb_search_inject", "sb_search_resample", "sb_search_wave", "sb_search_is_fused", "sb_search_stats",
+    "sb_search_inject", "sb_search_resample", "sb_search_seed_lpt", "sb_search_run", "sb_search_wave", "sb_search_is_fused", "sb_search_stats",
 ]
 
 
@@ -28,6 +28,19 @@ class SearchParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("chains", C.c_int64), ("chain_base", C.c_uint64),
                 ("flags", C.c_uint), ("t_start", C.c_float), ("t_end", C.c_float),
                 ("total_rounds", C.c_int)]
+
+
+class SearchControl(C.Structure):
+    _fields_ = [("rounds", C.c_int), ("resample_every", C.c_int), ("sync_every", C.c_int), ("patience", C.c_int),
+                ("heuristic_seeds", C.c_int), ("target_makespan", C.c_float), ("time_budget_s", C.c_double),
+                ("history_cap", C.c_int), ("history_len", C.POINTER(C.c_int)),
+                ("history_wall_s", C.POINTER(C.c_double)), ("history_evaluated", C.POINTER(C.c_int64)),
+                ("history_makespan", C.POINTER(C.c_float))]
+
+
+class SearchResultC(C.Structure):
+    _fields_ = [("makespan", C.c_float), ("key", C.c_uint64), ("evaluated", C.c_int64), ("rounds", C.c_int),
+                ("stop_reason", C.c_int), ("wall_s", C.c_double)]
 
 
 class SaturnB200Error(RuntimeError):
@@ -74,6 +87,9 @@ def load():
         "sb_search_best": [vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)],
         "sb_search_inject": [vp, vp, vp, i64, ci],
         "sb_search_resample": [vp],
+        "sb_search_seed_lpt": [vp],
+        "sb_search_run": [vp, C.POINTER(SearchParams), C.POINTER(SearchControl), vp, vp, vp, vp,
+                          C.POINTER(SearchResultC)],
         "sb_search_wave": [vp, C.c_uint, C.POINTER(i64)],
         "sb_search_is_fused": [vp],
         "sb_search_stats": [vp, C.POINTER(i64), C.POINTER(i64)],

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <chrono>
 #include <new>
 #include <utility>
 #include <vector>
@@ -803,6 +805,145 @@ int sb_search_inject(sb_handle* h, const uint8_t* opt, const void* prio, int64_t
   CK(search_keep_best(s.d, true, h->stream));
   CK(cudaStreamSynchronize(h->stream));  // opt / prio are caller memory: do not return with copies in flight
   s.evaluated += copies;
+  return SB_OK;
+}
+
+int sb_search_seed_lpt(sb_handle* h) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  const int J = h->J, nodes = h->nodes;
+  const bool reduced = (s.p.flags & SB_FLAG_REDUCED) != 0;
+  const float* tmin = h->h_tmin.data();
+  const double INF = HUGE_VAL;
+  // usable cells: below the sentinel threshold; a job with none falls back to any finite cell
+  std::vector<double> usable(static_cast<size_t>(J) * kSlots);
+  bool every_job = true;
+  for (int j = 0; j < J; ++j) {
+    bool any = false;
+    for (int c = 0; c < kSlots; ++c) {
+      const float v = tmin[j * kSlots + c];
+      usable[j * kSlots + c] = (v < h->sentinel) ? v : INF;
+      any = any || (v < h->sentinel);
+    }
+    every_job = every_job && any;
+  }
+  if (!every_job)
+    for (size_t i = 0; i < usable.size(); ++i) usable[i] = isfinite(tmin[i]) ? tmin[i] : INF;
+  const long long chains = s.d.chains;
+  const long long per = std::max<long long>(1, chains / 8);
+  std::vector<int> col(J), order(J);
+  std::vector<double> rt(J), weight(J);
+  std::vector<uint8_t> opt(J);
+  std::vector<uint16_t> prio16(J);
+  std::vector<uint8_t> prio8(J);
+  const double area_weights[3] = {0.0, 1.0, 0.5};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < J; ++j) {
+      int best = 0;
+      double bc = usable[j * kSlots] * pow(1.0, area_weights[i]);
+      for (int c = 1; c < kSlots; ++c) {
+        const double cost = usable[j * kSlots + c] * pow(c + 1.0, area_weights[i]);
+        if (cost < bc) { bc = cost; best = c; }
+      }
+      col[j] = best;
+      rt[j] = usable[j * kSlots + best];
+      weight[j] = rt[j] * sqrt(best + 1.0);
+      order[j] = j;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<double> load(nodes, 0.0);
+    for (int j = 0; j < J; ++j) opt[j] = static_cast<uint8_t>(col[j]);
+    if (nodes > 1) {
+      for (int q = 0; q < J; ++q) {
+        const int j = order[q];
+        int n = 0;
+        for (int m = 1; m < nodes; ++m)
+          if (load[m] < load[n]) n = m;
+        load[n] += rt[j] * (col[j] + 1);
+        opt[j] = static_cast<uint8_t>(col[j] | (n << 3));
+      }
+    } else if (!reduced) {
+      for (int j = 0; j < J; ++j) opt[j] = static_cast<uint8_t>((h->h_args[j * kSlots + col[j]] << 3) | col[j]);
+    }
+    for (int q = 0; q < J; ++q) { prio8[q] = static_cast<uint8_t>(order[q]); prio16[q] = static_cast<uint16_t>(order[q]); }
+    const long long first = std::min<long long>(i * per, std::max<long long>(0, chains - per));
+    const int copies = static_cast<int>(std::min<long long>(per, chains));
+    const void* pr = s.d.pb == 1 ? static_cast<const void*>(prio8.data()) : static_cast<const void*>(prio16.data());
+    if ((rc = sb_search_inject(h, opt.data(), pr, first, copies))) return rc;
+  }
+  return SB_OK;
+}
+
+int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_control* c, const uint8_t* warm_opt,
+                  const void* warm_prio, uint8_t* opt_out, void* prio_out, sb_search_result* result) {
+  if (!h || !p || !c) return fail(SB_ERR_ARG, "null argument");
+  if (c->rounds < 1 || c->sync_every < 1 || c->resample_every < 0 || c->patience < 0)
+    return fail(SB_ERR_ARG, "rounds / sync_every must be >= 1, resample_every / patience >= 0");
+  const auto t0 = std::chrono::steady_clock::now();
+  auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+  sb_search_params pp = *p;
+  pp.total_rounds = c->rounds;
+  int rc = sb_search_init(h, &pp, warm_opt, warm_prio);
+  if (rc) return rc;
+  if (c->heuristic_seeds && (rc = sb_search_seed_lpt(h))) return rc;
+  SearchState& s = h->search;
+  int hist = 0;
+  auto read_key = [&](unsigned long long* key) -> int {
+    CK(cudaMemcpyAsync(key, s.d.keys + 1, sizeof(*key), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SB_OK;
+  };
+  auto record = [&](unsigned long long key) {
+    if (c->history_cap > 0 && hist < c->history_cap) {
+      uint32_t bits = static_cast<uint32_t>(key >> 32);
+      float mk;
+      memcpy(&mk, &bits, 4);
+      if (c->history_wall_s) c->history_wall_s[hist] = elapsed();
+      if (c->history_evaluated) c->history_evaluated[hist] = s.evaluated;
+      if (c->history_makespan) c->history_makespan[hist] = mk;
+      ++hist;
+    }
+  };
+  unsigned long long best = 0, key = 0;
+  if ((rc = read_key(&best))) return rc;
+  record(best);
+  int done = 0, stale = 0, reason = 0;
+  while (done < c->rounds) {
+    const int step = std::min(c->sync_every, c->rounds - done);
+    int issued = 0;
+    while (issued < step) {
+      int n = step - issued;
+      if (c->resample_every) n = std::min(n, c->resample_every - ((done + issued) % c->resample_every));
+      if ((rc = sb_search_round(h, n))) return rc;
+      issued += n;
+      const int at = done + issued;
+      if (c->resample_every && at % c->resample_every == 0 && at < c->rounds && (rc = sb_search_resample(h))) return rc;
+    }
+    done += step;
+    if ((rc = read_key(&key))) return rc;
+    if (key < best) { best = key; stale = 0; } else { stale += step; }
+    record(best);
+    uint32_t bits = static_cast<uint32_t>(best >> 32);
+    float mk;
+    memcpy(&mk, &bits, 4);
+    if (c->time_budget_s > 0 && elapsed() > c->time_budget_s) { reason = 1; break; }
+    if (c->patience > 0 && stale >= c->patience) { reason = 2; break; }
+    if (c->target_makespan > 0 && mk <= c->target_makespan) { reason = 3; break; }
+  }
+  float mk = 0.f;
+  uint64_t k64 = 0;
+  if ((rc = sb_search_best(h, opt_out, prio_out, &mk, &k64))) return rc;
+  if (c->history_len) *c->history_len = hist;
+  if (result) {
+    result->makespan = mk;
+    result->key = k64;
+    result->evaluated = s.evaluated;
+    result->rounds = done;
+    result->stop_reason = reason;
+    result->wall_s = elapsed();
+  }
   return SB_OK;
 }
 

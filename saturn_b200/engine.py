@@ -242,6 +242,47 @@ class Engine:
         self._search_chains = chains
         self._search_base = chain_base
 
+    def search_seed_lpt(self):
+        """Plant the three longest-processing-time seeds into an eighth of the population each."""
+        check(self._lib.sb_search_seed_lpt(self._h))
+
+    def search_run(self, chains: int, rounds: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
+                   reduced: bool = False, t_start: float = 5e-4, t_end: float = 1e-6,
+                   warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, resample_every: int = 4, sync_every: int = 16,
+                   patience: int = 0, time_budget_s: float = 0.0, target_makespan: float = 0.0,
+                   heuristic_seeds: bool = True, record_history: bool = False, _no_fused: bool = False):
+        """The whole single-GPU search in one C call (sb_search_run).  Returns a dict: opt, prio, makespan, key,
+        evaluated, rounds, stop_reason, wall_s, history [(wall s, evaluated, makespan)]."""
+        J = self.J
+        pdt = np.uint8 if J <= 256 else np.uint16
+        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base,
+                         flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
+                         t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1))
+        cap = (max(rounds, 1) // max(1, sync_every) + 3) if record_history else 0
+        hw, he, hm = np.zeros(cap, np.float64), np.zeros(cap, np.int64), np.zeros(cap, np.float32)
+        hl = C.c_int(0)
+        ctl = _lib.SearchControl(rounds=max(rounds, 1), resample_every=int(resample_every), sync_every=max(1, int(sync_every)),
+                                 patience=int(patience or 0), heuristic_seeds=1 if heuristic_seeds else 0,
+                                 target_makespan=float(target_makespan or 0.0), time_budget_s=float(time_budget_s or 0.0),
+                                 history_cap=cap, history_len=C.pointer(hl),
+                                 history_wall_s=hw.ctypes.data_as(C.POINTER(C.c_double)),
+                                 history_evaluated=he.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 history_makespan=hm.ctypes.data_as(C.POINTER(C.c_float)))
+        wo = wp = None
+        keep = None
+        if warm is not None:
+            keep = (np.ascontiguousarray(warm[0], dtype=np.uint8), np.ascontiguousarray(warm[1], dtype=pdt))
+            wo, wp = C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data)
+        opt, prio = np.empty(J, dtype=np.uint8), np.empty(J, dtype=pdt)
+        res = _lib.SearchResultC()
+        check(self._lib.sb_search_run(self._h, C.byref(p), C.byref(ctl), wo, wp, C.c_void_p(opt.ctypes.data),
+                                      C.c_void_p(prio.ctypes.data), C.byref(res)))
+        del keep
+        n = int(hl.value)
+        return {"opt": opt, "prio": prio, "makespan": float(res.makespan), "key": int(res.key),
+                "evaluated": int(res.evaluated), "rounds": int(res.rounds), "stop_reason": int(res.stop_reason),
+                "wall_s": float(res.wall_s), "history": [(float(hw[i]), int(he[i]), float(hm[i])) for i in range(n)]}
+
     def search_wave(self, reduced: bool = False) -> int:
         """Chains that fill the device exactly once with the round kernel of the current table; populations
         that are whole multiples of it leave no partially filled last wave."""

@@ -77,7 +77,7 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
                target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 4,
                record_history: bool = False, heuristic_seeds: bool = True,
-               exchange_every: int = 16, _no_fused: bool = False) -> SearchResult:
+               exchange_every: int = 16, _no_fused: bool = False, _python_driver: bool = False) -> SearchResult:
     """Run the search on `engine` (table already set).  Returns the best candidate found by any rank.
 
     `rounds` device rounds are issued in groups of `exchange_every` (tournament resampling every
@@ -85,6 +85,15 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     their best key (one MIN) and the stopping rules are evaluated, so the host synchronises once per
     group rather than once per round."""
     dist = _dist() if use_dist else None
+    if dist is None and not reseed_every and not _python_driver and hasattr(engine, "search_run"):
+        # one process, one GPU: the same loop runs inside the library (sb_search_run)
+        r = engine.search_run(chains, rounds, seed=seed, integer_starts=integer_starts, reduced=reduced,
+                              t_start=t_start, t_end=t_end, warm=warm, resample_every=resample_every,
+                              sync_every=exchange_every, patience=patience or 0, time_budget_s=time_budget_s or 0.0,
+                              target_makespan=target_makespan or 0.0, heuristic_seeds=heuristic_seeds,
+                              record_history=record_history, _no_fused=_no_fused)
+        return SearchResult(opt=r["opt"], prio=r["prio"], makespan=r["makespan"], evaluated=r["evaluated"],
+                            rounds=r["rounds"], wall_s=r["wall_s"], history=r["history"], owner_rank=0)
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
     J = engine.J

@@ -19,7 +19,7 @@ tasks = [Task("t%d" % j, {g + 1: Strategy("x", g + 1, {}, float(tmin[j, g])) for
          for j in range(256)]
 solve(tasks, None, rounds=8)
 print("wave", solver._engine().search_wave(reduced=True))
-for chains in (131072, None, 131072, None):
+for chains in (131072, None, 131072, None) + (None,) * 12:
     t0 = time.perf_counter()
     out = solve(tasks, None, chains=chains, rounds=400)
     dt = time.perf_counter() - t0

@@ -247,3 +247,30 @@ def test_solve_reaches_the_exhaustive_optimum_on_random_small_instances():
         tab, om = R.table_from_tuples(tuples)
         best = R.brute_force(tab, om, True, nodes=nodes)[0]
         assert mk == pytest.approx(best, rel=1e-9), (trial, J, nodes, tuples)
+
+
+@pytest.mark.parametrize("J,S,nodes", [(64, 6, 1), (200, 1, 2), (600, 1, 1)])
+def test_library_search_loop_equals_python_driver(engine, J, S, nodes):
+    """sb_search_run (initialise, LPT seeds, rounds with resampling, stopping rules, all inside the library) and the
+    Python driver used for the multi-GPU case issue the same device work: same seeds -> the same incumbent."""
+    from saturn_b200.search import run_search
+    T, valid = R.synth_table(J, S, 8, seed=21, masked=(S > 1))
+    engine.set_table(T, nodes=nodes)
+    reduced = S == 1
+    kw = dict(chains=4096, rounds=48, seed=9, reduced=reduced, use_dist=False, record_history=True, exchange_every=8)
+    a = run_search(engine, **kw)
+    b = run_search(engine, _python_driver=True, **kw)
+    assert a.makespan == b.makespan and np.array_equal(a.opt, b.opt) and np.array_equal(a.prio, b.prio)
+    assert a.rounds == b.rounds == 48 and len(a.history) == len(b.history) == 7
+    assert [h[2] for h in a.history] == [h[2] for h in b.history]
+    tab = R.canon_table(T, range(1, 9))
+    if reduced:
+        tab = R.reduce_table(tab)[0][:, None, :]
+    assert R.list_schedule(tab, a.opt, a.prio, True, np.float32, nodes=nodes)[0] == a.makespan
+    # stopping rules: a target that the seeds already meet stops after the first group; patience stops a frozen search
+    c = run_search(engine, chains=4096, rounds=400, seed=9, reduced=reduced, use_dist=False, target_makespan=a.makespan * 2,
+                   exchange_every=8)
+    assert c.rounds == 8
+    d = run_search(engine, chains=64, rounds=4000, seed=9, reduced=reduced, use_dist=False, t_start=0.0, t_end=0.0,
+                   patience=64, exchange_every=8)
+    assert d.rounds < 4000
