@@ -43,6 +43,7 @@ struct SearchState {
   int rounds_done = 0;
   bool fused_ok = true;  // run rounds with the fused kernel while its tiles fit
   uint8_t *cand_o = nullptr, *cand_p = nullptr;  // device scratch for injected candidates
+  unsigned* tail_counter = nullptr;              // keep-best in the fused round's tail (SearchFuse::KeepBest)
   void* blocks[16];
   int nblocks = 0;
 };
@@ -103,6 +104,7 @@ static void free_search(sb_handle* h) {
   s.ready = false;
   s.d = SearchDev();
   s.cand_o = s.cand_p = nullptr;
+  s.tail_counter = nullptr;
 }
 
 static void free_staging(sb_handle* h) {
@@ -636,6 +638,8 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_p), d.stride_p))) return rc;
   if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_o), d.stride_o))) return rc;
   if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_p), d.stride_p))) return rc;
+  if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.tail_counter), sizeof(unsigned)))) return rc;
+  CK(cudaMemsetAsync(s.tail_counter, 0, sizeof(unsigned), h->stream));
   CK(cudaMemsetAsync(d.keys, 0xff, 2 * sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(d.cur_o, 0, P * d.stride_o, h->stream));
   CK(cudaMemsetAsync(d.cur_p, 0, P * d.stride_p, h->stream));
@@ -674,6 +678,19 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   return SB_OK;
 }
 
+static SearchFuse make_fuse(const SearchState& s, int round, float temperature) {
+  SearchFuse sf;
+  sf.cur_mk = s.d.cur_mk; sf.cur_o = s.d.cur_o; sf.cur_p = s.d.cur_p;
+  sf.vopt = s.d.vopt; sf.nvalid = s.d.nvalid;
+  sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
+  sf.temperature = temperature;
+  sf.keep.counter = s.tail_counter;
+  sf.keep.keys = s.d.keys;
+  sf.keep.best_o = s.d.best_o; sf.keep.best_p = s.d.best_p;
+  sf.keep.chains = s.d.chains; sf.keep.stride_o = s.d.stride_o; sf.keep.stride_p = s.d.stride_p;
+  return sf;
+}
+
 int sb_search_round(sb_handle* h, int rounds) {
   int rc = use_device(h);
   if (rc) return rc;
@@ -690,30 +707,20 @@ int sb_search_round(sb_handle* h, int rounds) {
     const float temperature = tf * s.scale;
     bool fused = false;
     if (s.d.pos) {
-      SearchFuse sf;
-      sf.cur_mk = s.d.cur_mk; sf.cur_o = s.d.cur_o; sf.cur_p = s.d.cur_p;
-      sf.vopt = s.d.vopt; sf.nvalid = s.d.nvalid;
-      sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
-      sf.temperature = temperature;
+      const SearchFuse sf = make_fuse(s, round, temperature);
       const bool reduced = (s.p.flags & SB_FLAG_REDUCED) != 0;
       CK(search_pos_launch(h->dev, s.d, reduced ? h->tmin : h->tab, (reduced ? 1 : h->S) * kSlots, s.p.flags, 0,
-                           s.d.chains, false, sf, h->stream));
-      CK(search_keep_best(s.d, true, h->stream));
+                           s.d.chains, false, sf, h->stream));  // keeps the incumbent in its tail
       fused = true;
     } else if (s.fused_ok) {
       EvalCall c;
       if ((rc = make_call(h, s.d.cur_o, s.d.cur_p, s.d.chains, s.d.stride_o, s.p.flags, &c))) return rc;
       c.best_key = s.d.keys;
       c.id_base = static_cast<uint32_t>(s.d.chain_base);
-      SearchFuse sf;
-      sf.cur_mk = s.d.cur_mk; sf.cur_o = s.d.cur_o; sf.cur_p = s.d.cur_p;
-      sf.vopt = s.d.vopt; sf.nvalid = s.d.nvalid;
-      sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
-      sf.temperature = temperature;
+      const SearchFuse sf = make_fuse(s, round, temperature);
       cudaError_t e = search_round_launch(h->dev, c, sf, h->stream);
       if (e == cudaSuccess) {
-        fused = true;
-        CK(search_keep_best(s.d, true, h->stream));   // an improving proposal is always accepted: it is in cur
+        fused = true;  // an improving proposal is always accepted, so it is in cur: the kernel's tail saves it
       } else if (e != cudaErrorNotSupported) {
         return fail(SB_ERR_CUDA, "fused search round failed: %s", cudaGetErrorString(e));
       } else {

@@ -230,6 +230,10 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b0 + lane), lane);
   }
   if (!tab_ready && threadIdx.x == 0) mbar_wait(bar_tab, 0);  // never leave a bulk copy in flight
+  if (SEARCH) {
+    if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
+    return;
+  }
   if (a.xp.counter != nullptr) {
     // fused exchange: the CTA that finishes last has seen every atomicMin on best_key; it publishes
     // {key, round} in this rank's mailbox (local stores, release at system scope).  Peers read the

@@ -64,6 +64,14 @@ struct SearchFuse {
   int round = 0;
   int nodes = 1;
   float temperature = 0.f;
+  // keep-best in the kernel's tail (KeepBest::counter != nullptr): the CTA that finishes last copies the
+  // incumbent's rows when the population's best key improved — saves the separate one-warp launch per round
+  struct KeepBest {
+    unsigned* counter = nullptr;         // zero between launches
+    unsigned long long* keys = nullptr;  // [0] best key of the population, [1] key of the saved encoding
+    uint8_t *best_o = nullptr, *best_p = nullptr;
+    long long chains = 0, stride_o = 0, stride_p = 0;
+  } keep;
 };
 
 int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp, bool tab_global = false);

@@ -114,6 +114,33 @@ __device__ __forceinline__ void fold_best(unsigned long long* best_key, bool act
   }
 }
 
+// Tail of a fused search round: every thread's accepted row bytes are fenced, the CTA that finishes last
+// has therefore seen the whole round; its first warp saves the incumbent's rows if keys[0] improved on
+// keys[1] (what k_keep_best does as a separate launch for the unfused rounds).
+__device__ __forceinline__ void keep_best_tail(const SearchFuse& sf) {
+  __threadfence();
+  __syncthreads();
+  int mine = 0;
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(sf.keep.counter, 1u);
+    mine = done == gridDim.x - 1;
+    if (mine) *sf.keep.counter = 0;
+  }
+  if (!__syncthreads_or(mine) || threadIdx.x >= 32) return;
+  __threadfence();
+  const int lane = threadIdx.x;
+  const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(sf.keep.keys);
+  if (key >= *reinterpret_cast<volatile unsigned long long*>(sf.keep.keys + 1)) return;
+  const long long c = static_cast<long long>(((key & 0xffffffffull) - (sf.chain_base & 0xffffffffull)) & 0xffffffffull);
+  if (c >= sf.keep.chains) return;
+  const uint4* so = reinterpret_cast<const uint4*>(sf.cur_o + c * sf.keep.stride_o);
+  const uint4* sp = reinterpret_cast<const uint4*>(sf.cur_p + c * sf.keep.stride_p);
+  for (int i = lane; i * 16 < sf.keep.stride_o; i += 32) reinterpret_cast<uint4*>(sf.keep.best_o)[i] = __ldcg(so + i);
+  for (int i = lane; i * 16 < sf.keep.stride_p; i += 32) reinterpret_cast<uint4*>(sf.keep.best_p)[i] = __ldcg(sp + i);
+  __syncwarp();
+  if (lane == 0) sf.keep.keys[1] = key;
+}
+
 // ---- SEARCH variant: one Metropolis round fused into the tile kernel.  The rows a warp fetched
 // are the chains' CURRENT candidates; every lane applies its own random move to its private
 // shared-memory rows, scores the result, decides acceptance and — only when accepted — writes the

@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     }
     if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
   }
+  if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
 }
 
 // ------------------------------------------------------------------------------------------ host
