@@ -350,20 +350,22 @@ def main():
     # ---- one fused search round at a large population (diagnostic: the kernel the solver actually runs)
     search_leg = None
     if not args.no_e2e and args.config == "C4":
-        chains = 1 << 20
-        eng.search_init(chains, seed=rank, chain_base=rank * chains, integer_starts=ints, reduced=False,
+        wave = eng.search_wave(reduced=True)
+        chains = wave * max(1, round((1 << 20) / wave))      # ~1 M chains in whole waves of the round kernel
+        eng.search_init(chains, seed=rank, chain_base=rank * chains, integer_starts=ints, reduced=True,
                         t_start=5e-4, t_end=1e-6, total_rounds=64)
-        eng.search_round(4)
+        eng.search_round(8)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        eng.search_round(16)
+        eng.search_round(32)
         s1.record()
         torch.cuda.synchronize()
-        ms = s0.elapsed_time(s1) / 16
+        ms = s0.elapsed_time(s1) / 32
         search_leg = {"candidates_per_s_per_gpu": chains / (ms * 1e-3), "ms_per_round": ms, "chains_per_gpu": chains,
-                      "fused": eng.search_is_fused(),
-                      "what": "propose + evaluate + Metropolis accept of every chain, one kernel per round"}
+                      "fused": eng.search_is_fused(), "rounds_per_launch": 8,
+                      "what": "the round kernel solve() runs (min-over-strategies table): move + evaluate + Metropolis "
+                              "accept of every chain, 8 rounds per launch with the rows resident in shared memory"}
 
     if rank == 0:
         peak, peak_src = measured_peak()

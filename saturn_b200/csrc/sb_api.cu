@@ -46,6 +46,10 @@ struct SearchState {
   unsigned* tail_counter = nullptr;              // keep-best in the fused round's tail (SearchFuse::KeepBest)
   void* blocks[16];
   int nblocks = 0;
+  // the allocation is kept across sb_search_init / sb_set_table calls while its shape stays the same (a
+  // re-planning loop solves the same task set every interval: no cudaMalloc / cudaFree per solve)
+  long long alloc_chains = 0, alloc_stride_o = 0, alloc_stride_p = 0;
+  SearchDev alloc;  // the pointers as allocated (s.d's cur / prop pairs trade places when resampling)
 };
 
 struct sb_handle {
@@ -103,6 +107,8 @@ static void free_search(sb_handle* h) {
   s.nblocks = 0;
   s.ready = false;
   s.d = SearchDev();
+  s.alloc = SearchDev();
+  s.alloc_chains = s.alloc_stride_o = s.alloc_stride_p = 0;
   s.cand_o = s.cand_p = nullptr;
   s.tail_counter = nullptr;
 }
@@ -203,7 +209,7 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
     packed |= static_cast<uint64_t>(gcount[g]) << (8 * g);
   }
   CK(cudaStreamSynchronize(h->stream));
-  free_search(h);
+  h->search.ready = false;  // its buffers are reused by the next sb_search_init if the shape is unchanged
   free_table(h);
   const size_t nT = static_cast<size_t>(J) * S * G;
   const size_t ntab = static_cast<size_t>(J) * S * kSlots;
@@ -606,8 +612,8 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   if (!p) return fail(SB_ERR_ARG, "params is null");
   if (p->chains < 1 || p->chains > (1ll << 31)) return fail(SB_ERR_ARG, "chains=%lld out of range", (long long)p->chains);
   CK(cudaStreamSynchronize(h->stream));
-  free_search(h);
   SearchState& s = h->search;
+  s.ready = false;
   s.p = *p;
   if (s.p.total_rounds < 1) s.p.total_rounds = 1;
   const int J = h->J;
@@ -627,18 +633,31 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   d.vopt = h->vopt[reduced ? 1 : 0];
   d.nvalid = h->nvalid[reduced ? 1 : 0];
   const size_t P = static_cast<size_t>(d.chains);
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_o), P * d.stride_o))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_p), P * d.stride_p))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_o), P * d.stride_o))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_p), P * d.stride_p))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_mk), P * sizeof(float)))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_mk), P * sizeof(float)))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.keys), 2 * sizeof(unsigned long long)))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_o), d.stride_o))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_p), d.stride_p))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_o), d.stride_o))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_p), d.stride_p))) return rc;
-  if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.tail_counter), sizeof(unsigned)))) return rc;
+  if (s.nblocks > 0 && s.alloc_chains == d.chains && s.alloc_stride_o == d.stride_o && s.alloc_stride_p == d.stride_p) {
+    d.cur_o = s.alloc.cur_o; d.cur_p = s.alloc.cur_p; d.prop_o = s.alloc.prop_o; d.prop_p = s.alloc.prop_p;
+    d.cur_mk = s.alloc.cur_mk; d.prop_mk = s.alloc.prop_mk; d.keys = s.alloc.keys;
+    d.best_o = s.alloc.best_o; d.best_p = s.alloc.best_p;
+  } else {
+    const SearchDev shape = d;
+    const sb_search_params params = s.p;
+    free_search(h);
+    s.p = params;
+    d = shape;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_o), P * d.stride_o))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_p), P * d.stride_p))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_o), P * d.stride_o))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_p), P * d.stride_p))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.cur_mk), P * sizeof(float)))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.prop_mk), P * sizeof(float)))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.keys), 2 * sizeof(unsigned long long)))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_o), d.stride_o))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&d.best_p), d.stride_p))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_o), d.stride_o))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.cand_p), d.stride_p))) return rc;
+    if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.tail_counter), sizeof(unsigned)))) return rc;
+    s.alloc = d;
+    s.alloc_chains = d.chains; s.alloc_stride_o = d.stride_o; s.alloc_stride_p = d.stride_p;
+  }
   CK(cudaMemsetAsync(s.tail_counter, 0, sizeof(unsigned), h->stream));
   CK(cudaMemsetAsync(d.keys, 0xff, 2 * sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(d.cur_o, 0, P * d.stride_o, h->stream));
@@ -678,12 +697,24 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   return SB_OK;
 }
 
-static SearchFuse make_fuse(const SearchState& s, int round, float temperature) {
+static float round_temperature(const SearchState& s, int round) {
+  float frac = static_cast<float>(round - 1) / static_cast<float>(s.p.total_rounds > 1 ? s.p.total_rounds - 1 : 1);
+  if (frac > 1.f) frac = 1.f;
+  float tf;
+  if (s.p.t_start <= 0.f) tf = 0.f;
+  else if (s.p.t_end <= 0.f) tf = s.p.t_start * (1.f - frac);
+  else tf = s.p.t_start * powf(s.p.t_end / s.p.t_start, frac);
+  return tf * s.scale;
+}
+
+// rounds [round, round + n) in one launch
+static SearchFuse make_fuse(const SearchState& s, int round, int n) {
   SearchFuse sf;
   sf.cur_mk = s.d.cur_mk; sf.cur_o = s.d.cur_o; sf.cur_p = s.d.cur_p;
   sf.vopt = s.d.vopt; sf.nvalid = s.d.nvalid;
   sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
-  sf.temperature = temperature;
+  sf.nrounds = n;
+  for (int r = 0; r < n; ++r) sf.temperature[r] = round_temperature(s, round + r);
   sf.keep.counter = s.tail_counter;
   sf.keep.keys = s.d.keys;
   sf.keep.best_o = s.d.best_o; sf.keep.best_p = s.d.best_p;
@@ -696,18 +727,14 @@ int sb_search_round(sb_handle* h, int rounds) {
   if (rc) return rc;
   SearchState& s = h->search;
   if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
-  for (int r = 0; r < rounds; ++r) {
+  int left = rounds;
+  while (left > 0) {
     const int round = s.rounds_done + 1;
-    float frac = static_cast<float>(round - 1) / static_cast<float>(s.p.total_rounds > 1 ? s.p.total_rounds - 1 : 1);
-    if (frac > 1.f) frac = 1.f;
-    float tf;
-    if (s.p.t_start <= 0.f) tf = 0.f;
-    else if (s.p.t_end <= 0.f) tf = s.p.t_start * (1.f - frac);
-    else tf = s.p.t_start * powf(s.p.t_end / s.p.t_start, frac);
-    const float temperature = tf * s.scale;
+    int n = 1;  // rounds covered by this iteration
     bool fused = false;
     if (s.d.pos) {
-      const SearchFuse sf = make_fuse(s, round, temperature);
+      n = std::min(left, kMaxFusedRounds);
+      const SearchFuse sf = make_fuse(s, round, n);
       const bool reduced = (s.p.flags & SB_FLAG_REDUCED) != 0;
       CK(search_pos_launch(h->dev, s.d, reduced ? h->tmin : h->tab, (reduced ? 1 : h->S) * kSlots, s.p.flags, 0,
                            s.d.chains, false, sf, h->stream));  // keeps the incumbent in its tail
@@ -717,7 +744,8 @@ int sb_search_round(sb_handle* h, int rounds) {
       if ((rc = make_call(h, s.d.cur_o, s.d.cur_p, s.d.chains, s.d.stride_o, s.p.flags, &c))) return rc;
       c.best_key = s.d.keys;
       c.id_base = static_cast<uint32_t>(s.d.chain_base);
-      const SearchFuse sf = make_fuse(s, round, temperature);
+      n = std::min(left, kMaxFusedRounds);
+      const SearchFuse sf = make_fuse(s, round, n);
       cudaError_t e = search_round_launch(h->dev, c, sf, h->stream);
       if (e == cudaSuccess) {
         fused = true;  // an improving proposal is always accepted, so it is in cur: the kernel's tail saves it
@@ -726,16 +754,18 @@ int sb_search_round(sb_handle* h, int rounds) {
       } else {
         cudaGetLastError();
         s.fused_ok = false;
+        n = 1;
       }
     }
     if (!fused) {
       CK(search_propose(s.d, round, h->stream));
       if ((rc = search_eval(h, false, 0, s.d.chains))) return rc;
       CK(search_keep_best(s.d, false, h->stream));
-      CK(search_accept(s.d, round, temperature, h->stream));
+      CK(search_accept(s.d, round, round_temperature(s, round), h->stream));
     }
-    s.rounds_done = round;
-    s.evaluated += s.d.chains;
+    s.rounds_done = round + n - 1;
+    s.evaluated += s.d.chains * n;
+    left -= n;
   }
   return SB_OK;
 }

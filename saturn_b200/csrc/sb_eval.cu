@@ -164,13 +164,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       tab_ready = true;
     }
     // ---- one candidate per lane
-    float mk = 0.f;
-    Move mv;
-    mv.kind = 0; mv.a = 0; mv.b = 0;
-    if (SEARCH && active)
-      mv = apply_move<PB>(a.sf, a.J, a.sf.chain_base + static_cast<uint64_t>(b0 + lane), tile_o + lane * a.row_o,
-                          tile_p + lane * a.row_p);
-    if (active) {
+    auto evaluate = [&](const uint8_t* prio_row_s) -> float {
       st.reset(a.nodes);
       const int J = a.J;
       if (STREAM) {
@@ -191,7 +185,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
           q = nxt;
         }
       } else {
-        const uint4* prow = reinterpret_cast<const uint4*>(tile_p + lane * a.row_p);
+        const uint4* prow = reinterpret_cast<const uint4*>(prio_row_s);
         constexpr int STEPS = 16 / PB;  // jobs per 128-bit shared-memory read
         const int nch = (J + STEPS - 1) / STEPS;
         for (int c = 0; c < nch; ++c) {
@@ -208,26 +202,62 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
           }
         }
       }
-      mk = st.result();
-      if (!SEARCH) a.out[b0 + lane] = mk;
-    }
-    if (SEARCH && active) {
-      // Metropolis acceptance at this round's temperature; write back only what changed
+      return st.result();
+    };
+    if (!SEARCH) {
+      float mk = 0.f;
+      if (active) {
+        mk = evaluate(tile_p + lane * a.row_p);
+        a.out[b0 + lane] = mk;
+      }
+      if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b0 + lane), lane);
+    } else {
+      // ---- sf.nrounds Metropolis rounds on the rows of this tile, which stay in shared memory: a rejected
+      // move is undone in place, an accepted one writes its few changed bytes through to HBM.  The lane
+      // whose candidate lowers the global best key stops moving for the rest of the launch, so that the rows
+      // the tail saves (keep_best_tail) are the ones the key was scored on.
       const long long c = b0 + lane;
-      const float cm = a.sf.cur_mk[c];
-      bool acc = mk <= cm;
-      if (!acc && a.sf.temperature > 0.f && isfinite(mk)) {
-        const uint64_t r = rng_u64(a.sf.seed, a.sf.chain_base + static_cast<uint64_t>(c), 4ull * a.sf.round + 3);
-        const float u = (static_cast<uint32_t>(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
-        acc = u < __expf(-(mk - cm) / a.sf.temperature);
+      // lanes beyond the end of the population shadow lane 0's rows (read-only), so that the evaluation below
+      // runs converged on valid data in every lane
+      const int rl = active ? lane : 0;
+      uint8_t* orow_s = tile_o + rl * a.row_o;
+      uint8_t* prow_s = tile_p + rl * a.row_p;
+      st.orow = orow_s;
+      const uint64_t gid = a.sf.chain_base + static_cast<uint64_t>(c);
+      float cm = active ? a.sf.cur_mk[c] : 0.f;
+      bool moving = active;  // false from the round in which this lane lowers the global best key
+#pragma unroll 1
+      for (int r = 0; r < a.sf.nrounds; ++r) {
+        const int round = a.sf.round + r;
+        Move mv;
+        mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = 0;
+        if (moving) mv = apply_move<PB>(a.sf, round, a.J, gid, orow_s, prow_s);
+        __syncwarp();  // shadowing lanes read lane 0's rows
+        float mk = evaluate(prow_s);
+        if (moving) {
+          bool acc = mk <= cm;
+          const float temp = a.sf.temperature[r];
+          if (!acc && temp > 0.f && isfinite(mk)) {
+            const uint64_t rr = rng_u64(a.sf.seed, gid, 4ull * round + 3);
+            const float u = (static_cast<uint32_t>(rr >> 40) + 0.5f) * (1.0f / 16777216.0f);
+            acc = u < __expf(-(mk - cm) / temp);
+          }
+          if (acc) {
+            if (mv.kind != 0) {
+              write_back<PB>(mv, orow_s, prow_s, a.sf.cur_o + c * a.stride_o, a.sf.cur_p + c * a.stride_p);
+              a.sf.cur_mk[c] = mk;
+              cm = mk;
+            }
+          } else {
+            undo_move<PB>(mv, orow_s, prow_s);
+            mk = cm;
+          }
+        }
+        if (a.best_key != nullptr && fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(c), lane))
+          moving = false;
       }
-      if (acc && mv.kind != 0) {
-        write_back<PB>(mv, tile_o + lane * a.row_o, tile_p + lane * a.row_p, a.sf.cur_o + c * a.stride_o,
-                       a.sf.cur_p + c * a.stride_p);
-        a.sf.cur_mk[c] = mk;
-      }
+      st.orow = tile_o + lane * a.row_o;
     }
-    if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(b0 + lane), lane);
   }
   if (!tab_ready && threadIdx.x == 0) mbar_wait(bar_tab, 0);  // never leave a bulk copy in flight
   if (SEARCH) {
@@ -566,13 +596,14 @@ static cudaError_t dispatch_search(const Device& dev, const TileArgs& a, const T
   return launch(k_eval_tiles<PB, INT, false, false, true>);
 }
 
-// 2 = both rows of a candidate fit in shared memory for at least 4 warps: the tile kernel runs the fused
-// round (all moves); 0 = they do not: the search keeps a position-major population (sb_search.cu) or, when
-// even the table does not fit, runs unfused rounds
+// 2 = both rows of a candidate fit in shared memory for at least 8 warps: the tile kernel runs the fused
+// round (all moves); 0 = they do not: the search keeps a position-major population (sb_search.cu: 16 warps
+// at any J; already 1.5x faster per round at J = 400 where only 5 tile warps fit,
+// profiles/r01_search_round.md) or, when even the table does not fit, runs unfused rounds
 int search_round_mode(const Device& dev, int J, int SG, int nodes) {
   const int pb = J <= 256 ? 1 : 2;
   TilePlan tp;
-  return plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 4 ? 2 : 0;
+  return plan_tiles(dev, J, SG, pb, false, nodes, &tp) >= 8 ? 2 : 0;
 }
 
 cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st) {

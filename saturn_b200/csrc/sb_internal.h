@@ -54,6 +54,7 @@ struct EvalCall {
 };
 
 // what the fused search round needs besides an EvalCall (see k_eval_tiles<..., SEARCH = true>)
+constexpr int kMaxFusedRounds = 8;
 struct SearchFuse {
   float* cur_mk = nullptr;        // [chains] makespan of each chain's current candidate
   uint8_t* cur_o = nullptr;       // writable views of the rows the EvalCall reads
@@ -61,9 +62,10 @@ struct SearchFuse {
   const uint8_t* vopt = nullptr;  // [J][8] proposable opt bytes
   const int* nvalid = nullptr;    // [J]
   uint64_t seed = 0, chain_base = 0;
-  int round = 0;
+  int round = 0;    // first round of this launch (RNG counters are keyed by the round number)
+  int nrounds = 1;  // rounds run back to back inside one launch, the rows staying on chip (<= kMaxFusedRounds)
   int nodes = 1;
-  float temperature = 0.f;
+  float temperature[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // per round of this launch
   // keep-best in the kernel's tail (KeepBest::counter != nullptr): the CTA that finishes last copies the
   // incumbent's rows when the population's best key improved — saves the separate one-warp launch per round
   struct KeepBest {

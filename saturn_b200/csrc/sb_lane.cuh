@@ -104,14 +104,17 @@ __device__ __forceinline__ int prio_at(const uint32_t* w, int t) {
   return static_cast<int>(__byte_perm(w[t >> 1], 0u, (t & 1) ? 0x4432u : 0x4410u));
 }
 
-__device__ __forceinline__ void fold_best(unsigned long long* best_key, bool active, float mk, uint32_t id, int lane) {
+// Returns true in the one lane whose candidate lowered *best_key (false everywhere else).
+__device__ __forceinline__ bool fold_best(unsigned long long* best_key, bool active, float mk, uint32_t id, int lane) {
   const uint32_t bits = active ? __float_as_uint(mk) : 0xffffffffu;
   const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
   const uint32_t who = __ballot_sync(0xffffffffu, bits == mn);
+  bool lowered = false;
   if (lane == __ffs(who) - 1 && active) {
     const unsigned long long key = pack_key(mk, id);
-    if (key < *reinterpret_cast<volatile unsigned long long*>(best_key)) atomicMin(best_key, key);
+    if (key < *reinterpret_cast<volatile unsigned long long*>(best_key)) lowered = key < atomicMin(best_key, key);
   }
+  return lowered;
 }
 
 // Tail of a fused search round: every thread's accepted row bytes are fenced, the CTA that finishes last
@@ -149,7 +152,8 @@ __device__ __forceinline__ void keep_best_tail(const SearchFuse& sf) {
 struct Move {
   int kind;  // 0 none, 1 opt byte of job a changed, 2 positions a,b swapped, 3 positions [a..b] rewritten
   int a, b;
-  int va, vb;  // kind 2: the jobs that were at positions a and b
+  int va, vb;  // kind 1: va = the previous opt byte; kind 2: the jobs that were at positions a and b;
+               // kind 3: the job travelled from position va to position vb
 };
 
 __device__ __forceinline__ uint32_t bounded32(uint64_t r, uint32_t n) {
@@ -168,12 +172,13 @@ __device__ __forceinline__ void smem_prio_st(uint8_t* row, int i, int v) {
 
 // `orow` / `prow` are the lane's rows in SHARED memory: the move is applied in place.
 template <int PB>
-__device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t gid, uint8_t* orow, uint8_t* prow) {
+__device__ __forceinline__ Move apply_move(const SearchFuse& sf, int round, int J, uint64_t gid, uint8_t* orow,
+                                           uint8_t* prow) {
   Move m;
   m.kind = 0; m.a = 0; m.b = 0; m.va = 0; m.vb = 0;
-  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * sf.round + 0);
-  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * sf.round + 1);
-  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * sf.round + 2);
+  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * round + 0);
+  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * round + 1);
+  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * round + 2);
   const uint32_t kind = bounded32(r0, 100);
   if (sf.nodes > 1 && kind >= 85) {  // move one job to another node (milp.py:117-137)
     const int j = bounded32(r1, J);
@@ -181,7 +186,7 @@ __device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t
     int nn = bounded32(r2, sf.nodes - 1);
     if (nn >= (curv >> 3)) ++nn;
     orow[j] = static_cast<uint8_t>((curv & 7) | (nn << 3));
-    m.kind = 1; m.a = j;
+    m.kind = 1; m.a = j; m.va = curv;
     return m;
   }
   if (kind < 30) {  // change one job's option (keeping its node)
@@ -195,7 +200,7 @@ __device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t
       uint8_t nv = sf.vopt[j * kSlots + pick];
       if (nv == cur_opt) nv = sf.vopt[j * kSlots + n - 1];
       orow[j] = nv | node_bits;
-      m.kind = 1; m.a = j;
+      m.kind = 1; m.a = j; m.va = curv;
       return m;
     }
   }
@@ -224,8 +229,29 @@ __device__ __forceinline__ Move apply_move(const SearchFuse& sf, int J, uint64_t
     for (int i = a; i > b; --i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i - 1));
   }
   smem_prio_st<PB>(prow, b, va);
-  m.kind = 3; m.a = a < b ? a : b; m.b = a < b ? b : a;
+  m.kind = 3; m.a = a < b ? a : b; m.b = a < b ? b : a; m.va = a; m.vb = b;
   return m;
+}
+
+// A rejected move is taken back so that the rows in shared memory stay the chain's current candidate
+// (several rounds run on the same tile, see k_eval_tiles).
+template <int PB>
+__device__ __forceinline__ void undo_move(const Move& m, uint8_t* orow, uint8_t* prow) {
+  if (m.kind == 1) {
+    orow[m.a] = static_cast<uint8_t>(m.va);
+  } else if (m.kind == 2) {
+    smem_prio_st<PB>(prow, m.a, m.va);
+    smem_prio_st<PB>(prow, m.b, m.vb);
+  } else if (m.kind == 3) {
+    const int from = m.vb, to = m.va;  // the job sits at `from` and goes back to `to`
+    const int job = smem_prio_ld<PB>(prow, from);
+    if (from < to) {
+      for (int i = from; i < to; ++i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i + 1));
+    } else {
+      for (int i = from; i > to; --i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i - 1));
+    }
+    smem_prio_st<PB>(prow, to, job);
+  }
 }
 
 template <int PB>

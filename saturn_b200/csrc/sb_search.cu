@@ -248,13 +248,13 @@ struct PosMove {
 };
 
 template <int PB>
-__device__ __forceinline__ PosMove make_pos_move(const SearchFuse& sf, int J, uint64_t gid, const uint8_t* og,
-                                                 const uint8_t* pg) {
+__device__ __forceinline__ PosMove make_pos_move(const SearchFuse& sf, int round, int J, uint64_t gid,
+                                                 const uint8_t* og, const uint8_t* pg) {
   PosMove m;
   m.kind = 0; m.a = m.b = m.va = m.vb = m.oa = m.ob = 0;
-  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * sf.round + 0);
-  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * sf.round + 1);
-  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * sf.round + 2);
+  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * round + 0);
+  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * round + 1);
+  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * round + 2);
   const uint32_t kind = bounded(r0, 100);
   if (sf.nodes > 1 && kind >= 85) {  // move the job at a random position to another node
     const int p = bounded(r1, J);
@@ -323,13 +323,13 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
        tile += static_cast<long long>(gridDim.x) * nw) {
     const long long c = a.first + tile * 32 + lane;
     const bool active = tile * 32 + lane < a.chains;
-    float mk = 0.f;
-    PosMove mv;
-    mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = mv.oa = mv.ob = 0;
-    if (active) {
-      uint8_t* og = a.opt + c * a.stride_o;
-      uint8_t* pg = a.prio + c * a.stride_p;
-      if (!a.eval_only) mv = make_pos_move<PB>(a.sf, J, a.sf.chain_base + static_cast<uint64_t>(c), og, pg);
+    // lanes beyond the end of the population shadow lane 0's chain (read-only): the evaluation below then runs
+    // converged on valid rows in every lane
+    const long long cr = active ? c : a.first + tile * 32;
+    uint8_t* og = a.opt + cr * a.stride_o;
+    uint8_t* pg = a.prio + cr * a.stride_p;
+    // both rows stream through registers, with the proposed move patched into the chunks
+    auto evaluate = [&](const PosMove& mv) -> float {
       st.reset(a.nodes);
       const int nout = (J + 31) / 32;  // outer iterations of 32 positions
       PrioChunk qo = ld_prio32<false>(og);
@@ -379,16 +379,34 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
 #pragma unroll
         for (int h = 0; h < PCH; ++h) qp[h] = np[h];
       }
-      mk = st.result();
-      if (a.eval_only) {
-        a.sf.cur_mk[c] = mk;
-      } else {
-        const float cm = a.sf.cur_mk[c];
+      return st.result();
+    };
+    PosMove none;
+    none.kind = 0; none.a = none.b = none.va = none.vb = none.oa = none.ob = 0;
+    if (a.eval_only) {
+      const float mk = evaluate(none);
+      if (active) a.sf.cur_mk[c] = mk;
+      if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
+      continue;
+    }
+    // sf.nrounds rounds per launch: an accepted move is written to the rows, which the next round streams
+    // again; the lane that lowers the global best key stops moving (see k_eval_tiles)
+    float cm = active ? a.sf.cur_mk[c] : 0.f;
+    bool moving = active;  // false from the round in which this lane lowers the global best key
+    const uint64_t gid = a.sf.chain_base + static_cast<uint64_t>(c);
+#pragma unroll 1
+    for (int r = 0; r < a.sf.nrounds; ++r) {
+      const int round = a.sf.round + r;
+      PosMove mv = none;
+      if (moving) mv = make_pos_move<PB>(a.sf, round, J, gid, og, pg);
+      float mk = evaluate(mv);
+      if (moving) {
         bool acc = mk <= cm;
-        if (!acc && a.sf.temperature > 0.f && isfinite(mk)) {
-          const uint64_t r = rng_u64(a.sf.seed, a.sf.chain_base + static_cast<uint64_t>(c), 4ull * a.sf.round + 3);
-          const float u = (static_cast<uint32_t>(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
-          acc = u < __expf(-(mk - cm) / a.sf.temperature);
+        const float temp = a.sf.temperature[r];
+        if (!acc && temp > 0.f && isfinite(mk)) {
+          const uint64_t rr = rng_u64(a.sf.seed, gid, 4ull * round + 3);
+          const float u = (static_cast<uint32_t>(rr >> 40) + 0.5f) * (1.0f / 16777216.0f);
+          acc = u < __expf(-(mk - cm) / temp);
         }
         if (acc && mv.kind != 0) {
           if (mv.kind == 1) {
@@ -400,10 +418,14 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
             prio_st<PB>(pg, mv.b, mv.va);
           }
           a.sf.cur_mk[c] = mk;
+          cm = mk;
+        } else if (!acc) {
+          mk = cm;
         }
       }
+      if (a.best_key != nullptr && fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane))
+        moving = false;
     }
-    if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
   }
   if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
 }
