@@ -375,8 +375,8 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": dram if args.config == "C4" else None, "eval_path": kernel_path, "kernel": "k_eval_tiles<1,%s,true>" % ("true" if ints else "false"),
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                "note": "instruction-issue bound, not HBM bound: one list-scheduling step is ~57 SASS "
-                        "instructions per candidate for 2 bytes of input (89 % of issue slots used); see "
+                "note": "instruction-issue bound, not HBM bound: one list-scheduling step is ~53 SASS "
+                        "instructions per warp of 32 candidates for 64 bytes of input (89 % of issue slots used); see "
                         "DESIGN.md 5.1 and profiles/r01_summary.md"}
         cpu = None
         if world == 1 and not args.no_cpu:
