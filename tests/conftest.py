@@ -74,3 +74,18 @@ def tasks_from_tuples(tuples, executor="exec"):
     for t, tup in enumerate(tuples):
         out.append(DuckTask("t%d" % t, {int(g): Strategy(executor, int(g), {}, float(rt)) for g, rt in tup}))
     return out
+
+
+def build_c_host(out_dir):
+    """Compile examples/c_host.c (plain C, -Wall -Werror) against include/saturn_b200.h and link it with the
+    in-tree library; returns the binary's path."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from saturn_b200 import _lib
+    libdir = os.path.dirname(_lib.SO_PATH)
+    exe = os.path.join(str(out_dir), "c_host")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_host.c"), "-L", libdir, "-lsaturn_b200",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True, capture_output=True)
+    return exe

@@ -274,3 +274,40 @@ def test_library_search_loop_equals_python_driver(engine, J, S, nodes):
     d = run_search(engine, chains=64, rounds=4000, seed=9, reduced=reduced, use_dist=False, t_start=0.0, t_end=0.0,
                    patience=64, exchange_every=8)
     assert d.rounds < 4000
+
+
+@pytest.mark.parametrize("J", [24, 300])
+def test_plain_c_host_plans_through_the_abi(tmp_path, J):
+    """examples/c_host.c — sb_create / sb_set_table / sb_search_run / sb_decode from C, no Python in the loop.
+    The plan it prints is re-scored by the oracle on the table it prints: same makespan, feasible, and not
+    worse than a longest-processing-time list schedule."""
+    import subprocess
+    from conftest import build_c_host
+    out = subprocess.run([build_c_host(tmp_path), str(J), "11"], capture_output=True, text=True, check=True).stdout
+    lines = out.splitlines()
+    hdr = lines[0].split()
+    Jp, S, G = int(hdr[1]), int(hdr[3]), int(hdr[5])
+    assert Jp == J
+    T = np.array(lines[1].split()[1:], dtype=np.float32).reshape(J, S, G)
+    mk = float(lines[2].split()[1])
+    assert float(lines[2].split()[3]) == mk                      # the decode re-derives the search's makespan
+    opt = np.array(lines[3].split()[1:], dtype=np.uint8)
+    prio = np.array(lines[4].split()[1:], dtype=np.int64)
+    assert sorted(prio.tolist()) == list(range(J))
+    tmin = R.reduce_table(R.canon_table(T, range(1, 9)))[0]
+    got, start, mask, _ = R.list_schedule(tmin[:, None, :], opt, prio, True, np.float32)
+    assert np.float32(got) == np.float32(mk)
+    jobs = [l.split() for l in lines[5:5 + J]]
+    assert [int(j[1]) for j in jobs] == list(range(J))
+    k = np.array([int(j[5]) for j in jobs])
+    assert np.array_equal(k, (opt & 7) + 1)
+    assert np.array_equal(np.array([float(j[7]) for j in jobs], dtype=np.float32), np.asarray(start, dtype=np.float32))
+    assert np.array_equal(np.array([int(j[9], 16) for j in jobs]), np.asarray(mask) & 0xff)
+    rt = tmin[np.arange(J), opt & 7]
+    ok, overlaps, _ = R.check_plan(start, mask, rt, k)
+    assert ok and overlaps == 0
+    # strategy = the arg-min strategy of the chosen GPU count (the profiler's min over executors)
+    assert np.array_equal(np.array([int(j[3]) for j in jobs]), np.argmin(T[np.arange(J), :, k - 1], axis=1))
+    lpt_order = np.argsort(-tmin[:, 7], kind="stable")
+    lpt = R.list_schedule(tmin[:, None, :], np.full(J, 7, np.uint8), lpt_order, True, np.float32)[0]
+    assert mk <= lpt

@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import DuckTask, tasks_from_tuples
+from conftest import DuckTask, build_c_host, tasks_from_tuples
 from oracle import ref_eval as R
 from saturn_b200 import HParams, Strategy, Task, Techniques, _lib
 from saturn_b200.orchestrator import forecast
@@ -24,6 +24,17 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), s
     assert _lib.load().sb_abi_version() == 1
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/saturn_b200.h compiles as C99 and a C host using only that header links against the library;
+    without a GPU the host fails loudly at sb_create (no CPU path)."""
+    import subprocess
+    import torch
+    exe = build_c_host(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "4"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr
 
 
 def test_no_cpu_fallback_fails_loudly():
