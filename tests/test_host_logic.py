@@ -37,6 +37,28 @@ def test_header_is_plain_c_and_a_c_host_links(tmp_path):
         assert r.returncode == 1 and "no CPU path" in r.stderr
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors of the ABI's structs have the field offsets and sizes the C compiler gives them."""
+    import subprocess
+    structs = {"sb_search_params": _lib.SearchParams, "sb_search_control": _lib.SearchControl,
+               "sb_search_result": _lib.SearchResultC}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "saturn_b200.h"\nint main(void) {\n%s\nreturn 0; }\n'
+                   % "\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_no_cpu_fallback_fails_loudly():
     import torch
     if torch.cuda.is_available():
