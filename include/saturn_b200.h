@@ -190,6 +190,12 @@ typedef struct sb_search_params {
   float t_start;        /* initial temperature as a fraction of the incumbent makespan */
   float t_end;          /* final temperature fraction */
   int total_rounds;     /* cooling horizon */
+  int resample_every;   /* > 0: sb_search_round itself resamples the population by tournament before every round r
+                         * with (r - 1) % resample_every == 0 — inside the round kernel where the rows are resident
+                         * in shared memory (rivals = the 32 chains of a warp, re-dealt between launches), with the
+                         * sb_search_resample kernel otherwise.  0: only when the caller calls sb_search_resample.  -1: automatic
+                         * (2 where the tournament runs inside the round kernel, 4 where it is a copy of the population;
+                         * profiles/r01_search_round.md). */
 } sb_search_params;
 
 int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_opt /*host, nullable*/,
@@ -218,7 +224,7 @@ int sb_search_resample(sb_handle* h);
  * The multi-GPU driver (saturn_b200/search.py) runs the same steps with a key exchange per group. */
 typedef struct sb_search_control {
   int rounds;             /* >= 1 */
-  int resample_every;     /* 0 = never */
+  int resample_every;     /* 0 = never, -1 = automatic; overrides sb_search_params.resample_every */
   int sync_every;         /* rounds per group, >= 1 */
   int patience;           /* stop after this many rounds without improvement; 0 = off */
   int heuristic_seeds;    /* 1 = sb_search_seed_lpt after initialisation */

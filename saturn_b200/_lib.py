@@ -27,7 +27,7 @@ SYMBOLS = [
 class SearchParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("chains", C.c_int64), ("chain_base", C.c_uint64),
                 ("flags", C.c_uint), ("t_start", C.c_float), ("t_end", C.c_float),
-                ("total_rounds", C.c_int)]
+                ("total_rounds", C.c_int), ("resample_every", C.c_int)]
 
 
 class SearchControl(C.Structure):

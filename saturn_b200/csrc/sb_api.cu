@@ -44,6 +44,7 @@ struct SearchState {
   bool fused_ok = true;  // run rounds with the fused kernel while its tiles fit
   uint8_t *cand_o = nullptr, *cand_p = nullptr;  // device scratch for injected candidates
   unsigned* tail_counter = nullptr;              // keep-best in the fused round's tail (SearchFuse::KeepBest)
+  long long launches = 0;                        // fused launches so far (the deal of chains to warps alternates)
   void* blocks[16];
   int nblocks = 0;
   // the allocation is kept across sb_search_init / sb_set_table calls while its shape stays the same (a
@@ -693,7 +694,10 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   s.scale = isfinite(mk) ? mk : 1.0f;
   s.evaluated = d.chains;
   s.rounds_done = 0;
+  s.launches = 0;
   s.fused_ok = d.pos || (!no_fused && mode != 0);
+  // automatic cadence: resampling is nearly free inside the tile kernel, a full copy of the population elsewhere
+  if (s.p.resample_every < 0) s.p.resample_every = (s.fused_ok && !d.pos) ? 2 : 4;
   return SB_OK;
 }
 
@@ -715,6 +719,8 @@ static SearchFuse make_fuse(const SearchState& s, int round, int n) {
   sf.seed = s.d.seed; sf.chain_base = s.d.chain_base; sf.round = round; sf.nodes = s.d.nodes;
   sf.nrounds = n;
   for (int r = 0; r < n; ++r) sf.temperature[r] = round_temperature(s, round + r);
+  sf.resample_every = s.p.resample_every > 0 ? s.p.resample_every : 0;
+  sf.deal = static_cast<int>(s.launches & 1);
   sf.keep.counter = s.tail_counter;
   sf.keep.keys = s.d.keys;
   sf.keep.best_o = s.d.best_o; sf.keep.best_p = s.d.best_p;
@@ -727,14 +733,22 @@ int sb_search_round(sb_handle* h, int rounds) {
   if (rc) return rc;
   SearchState& s = h->search;
   if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  const int re = s.p.resample_every > 0 ? s.p.resample_every : 0;
   int left = rounds;
   while (left > 0) {
     const int round = s.rounds_done + 1;
     int n = 1;  // rounds covered by this iteration
     bool fused = false;
+    const bool due = re > 0 && round > 1 && (round - 1) % re == 0;  // the population is resampled before this round
     if (s.d.pos) {
+      if (due) {
+        CK(search_resample(s.d, s.rounds_done, h->stream));
+        std::swap(s.d.cur_o, s.d.prop_o); std::swap(s.d.cur_p, s.d.prop_p); std::swap(s.d.cur_mk, s.d.prop_mk);
+      }
       n = std::min(left, kMaxFusedRounds);
-      const SearchFuse sf = make_fuse(s, round, n);
+      if (re > 0) n = std::min(n, re - (round - 1) % re);  // up to the next resampling point
+      SearchFuse sf = make_fuse(s, round, n);
+      sf.resample_every = 0;
       const bool reduced = (s.p.flags & SB_FLAG_REDUCED) != 0;
       CK(search_pos_launch(h->dev, s.d, reduced ? h->tmin : h->tab, (reduced ? 1 : h->S) * kSlots, s.p.flags, 0,
                            s.d.chains, false, sf, h->stream));  // keeps the incumbent in its tail
@@ -745,10 +759,11 @@ int sb_search_round(sb_handle* h, int rounds) {
       c.best_key = s.d.keys;
       c.id_base = static_cast<uint32_t>(s.d.chain_base);
       n = std::min(left, kMaxFusedRounds);
-      const SearchFuse sf = make_fuse(s, round, n);
+      const SearchFuse sf = make_fuse(s, round, n);  // resamples inside the kernel
       cudaError_t e = search_round_launch(h->dev, c, sf, h->stream);
       if (e == cudaSuccess) {
         fused = true;  // an improving proposal is always accepted, so it is in cur: the kernel's tail saves it
+        ++s.launches;
       } else if (e != cudaErrorNotSupported) {
         return fail(SB_ERR_CUDA, "fused search round failed: %s", cudaGetErrorString(e));
       } else {
@@ -758,6 +773,10 @@ int sb_search_round(sb_handle* h, int rounds) {
       }
     }
     if (!fused) {
+      if (due) {
+        CK(search_resample(s.d, s.rounds_done, h->stream));
+        std::swap(s.d.cur_o, s.d.prop_o); std::swap(s.d.cur_p, s.d.prop_p); std::swap(s.d.cur_mk, s.d.prop_mk);
+      }
       CK(search_propose(s.d, round, h->stream));
       if ((rc = search_eval(h, false, 0, s.d.chains))) return rc;
       CK(search_keep_best(s.d, false, h->stream));
@@ -916,12 +935,13 @@ int sb_search_seed_lpt(sb_handle* h) {
 int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_control* c, const uint8_t* warm_opt,
                   const void* warm_prio, uint8_t* opt_out, void* prio_out, sb_search_result* result) {
   if (!h || !p || !c) return fail(SB_ERR_ARG, "null argument");
-  if (c->rounds < 1 || c->sync_every < 1 || c->resample_every < 0 || c->patience < 0)
-    return fail(SB_ERR_ARG, "rounds / sync_every must be >= 1, resample_every / patience >= 0");
+  if (c->rounds < 1 || c->sync_every < 1 || c->resample_every < -1 || c->patience < 0)
+    return fail(SB_ERR_ARG, "rounds / sync_every must be >= 1, resample_every >= -1, patience >= 0");
   const auto t0 = std::chrono::steady_clock::now();
   auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
   sb_search_params pp = *p;
   pp.total_rounds = c->rounds;
+  pp.resample_every = c->resample_every;
   int rc = sb_search_init(h, &pp, warm_opt, warm_prio);
   if (rc) return rc;
   if (c->heuristic_seeds && (rc = sb_search_seed_lpt(h))) return rc;
@@ -949,15 +969,7 @@ int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_contr
   int done = 0, stale = 0, reason = 0;
   while (done < c->rounds) {
     const int step = std::min(c->sync_every, c->rounds - done);
-    int issued = 0;
-    while (issued < step) {
-      int n = step - issued;
-      if (c->resample_every) n = std::min(n, c->resample_every - ((done + issued) % c->resample_every));
-      if ((rc = sb_search_round(h, n))) return rc;
-      issued += n;
-      const int at = done + issued;
-      if (c->resample_every && at % c->resample_every == 0 && at < c->rounds && (rc = sb_search_resample(h))) return rc;
-    }
+    if ((rc = sb_search_round(h, step))) return rc;  // resamples on its own cadence (sb_search_params)
     done += step;
     if ((rc = read_key(&key))) return rc;
     if (key < best) { best = key; stale = 0; } else { stale += step; }

@@ -132,9 +132,12 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
   for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
        tile += static_cast<long long>(gridDim.x) * nw) {
     const long long b0 = tile * 32;
-    const int nb = static_cast<int>(min(32ll, a.B - b0));
-    const bool active = lane < nb;
-    const uint8_t* pg = a.prio + (b0 + lane) * a.stride_p;
+    // the candidate of this lane: consecutive ids, or (search rounds, sf.deal = 1) one id from each of 32
+    // far-apart blocks so that successive launches put different chains into one warp
+    const long long cand = (SEARCH && a.sf.deal) ? lane * a.ntiles + tile : b0 + lane;
+    const bool active = cand < a.B;
+    const int nb = SEARCH ? __popc(__ballot_sync(0xffffffffu, active)) : static_cast<int>(min(32ll, a.B - b0));
+    const uint8_t* pg = a.prio + cand * a.stride_p;
     // ---- fetch this warp's 32 candidate rows
     __syncwarp();
     PrioChunk q;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         mbar_arrive_expect_tx(bar_w, static_cast<uint32_t>(nb) * (a.copy_o + (STREAM ? 0 : a.copy_p)));
       __syncwarp();
       if (active) {
-        tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + (b0 + lane) * a.stride_o, a.copy_o, bar_w);
+        tma_bulk_g2s(tile_o + lane * a.row_o, a.opt + cand * a.stride_o, a.copy_o, bar_w);
         if (!STREAM) tma_bulk_g2s(tile_p + lane * a.row_p, pg, a.copy_p, bar_w);
       }
       if (STREAM && active) q = ld_prio32<true>(pg);  // overlaps the TMA wait
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       // move is undone in place, an accepted one writes its few changed bytes through to HBM.  The lane
       // whose candidate lowers the global best key stops moving for the rest of the launch, so that the rows
       // the tail saves (keep_best_tail) are the ones the key was scored on.
-      const long long c = b0 + lane;
+      const long long c = cand;
       // lanes beyond the end of the population shadow lane 0's rows (read-only), so that the evaluation below
       // runs converged on valid data in every lane
       const int rl = active ? lane : 0;
@@ -229,6 +232,36 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
 #pragma unroll 1
       for (int r = 0; r < a.sf.nrounds; ++r) {
         const int round = a.sf.round + r;
+        if (a.sf.resample_every > 0 && round > 1 && (round - 1) % a.sf.resample_every == 0) {
+          // tournament inside the warp: take over the rows of a random lane if its candidate is better.
+          // Rows move 16 bytes at a time through registers, every lane reading chunk i before any lane
+          // writes chunk i, so a lane that is both source and taker is still copied in its old state.
+          const uint64_t rr = rng_u64(a.sf.seed ^ 0x7e57a11ull, gid, static_cast<uint64_t>(round));
+          const int rival = static_cast<int>(rr >> 59);
+          const float rcm = __shfl_sync(0xffffffffu, cm, rival);
+          const bool ractive = (__ballot_sync(0xffffffffu, active) >> rival) & 1u;
+          const bool take = moving && ractive && rcm < cm;
+          const uint4* so = reinterpret_cast<const uint4*>(tile_o + rival * a.row_o);
+          const uint4* sp = reinterpret_cast<const uint4*>(tile_p + rival * a.row_p);
+          uint4* go = reinterpret_cast<uint4*>(a.sf.cur_o + c * a.stride_o);
+          uint4* gp = reinterpret_cast<uint4*>(a.sf.cur_p + c * a.stride_p);
+          for (int i = 0; i * 16 < a.copy_o; ++i) {
+            const uint4 v = so[i];
+            __syncwarp();
+            if (take) { reinterpret_cast<uint4*>(orow_s)[i] = v; go[i] = v; }
+            __syncwarp();
+          }
+          for (int i = 0; i * 16 < a.copy_p; ++i) {
+            const uint4 v = sp[i];
+            __syncwarp();
+            if (take) { reinterpret_cast<uint4*>(prow_s)[i] = v; gp[i] = v; }
+            __syncwarp();
+          }
+          if (take) {
+            cm = rcm;
+            a.sf.cur_mk[c] = rcm;
+          }
+        }
         Move mv;
         mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = 0;
         if (moving) mv = apply_move<PB>(a.sf, round, a.J, gid, orow_s, prow_s);

@@ -66,6 +66,11 @@ struct SearchFuse {
   int nrounds = 1;  // rounds run back to back inside one launch, the rows staying on chip (<= kMaxFusedRounds)
   int nodes = 1;
   float temperature[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // per round of this launch
+  // Tournament resampling inside the tile kernel: before every round r with (r - 1) % resample_every == 0
+  // (r > 1) each lane takes over the rows of a random lane of its warp if that lane's candidate is better.
+  // `deal` changes which chains share a warp: 0 = chain = tile * 32 + lane, 1 = chain = lane * ntiles + tile.
+  int resample_every = 0;
+  int deal = 0;
   // keep-best in the kernel's tail (KeepBest::counter != nullptr): the CTA that finishes last copies the
   // incumbent's rows when the population's best key improved — saves the separate one-warp launch per round
   struct KeepBest {

@@ -226,8 +226,10 @@ class Engine:
     # ------------------------------------------------------------------ search
     def search_init(self, chains: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
                     reduced: bool = False, t_start: float = 0.02, t_end: float = 1e-4, total_rounds: int = 200,
-                    warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, _no_fused: bool = False):
-        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base,
+                    warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, resample_every: int = 0,
+                    _no_fused: bool = False):
+        """resample_every > 0: search_round resamples the population by tournament on that cadence itself."""
+        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base, resample_every=int(resample_every or 0),
                          flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
                          t_start=t_start, t_end=t_end, total_rounds=total_rounds)
         wo = wp = None
@@ -248,7 +250,7 @@ class Engine:
 
     def search_run(self, chains: int, rounds: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
                    reduced: bool = False, t_start: float = 5e-4, t_end: float = 1e-6,
-                   warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, resample_every: int = 4, sync_every: int = 16,
+                   warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, resample_every: int = -1, sync_every: int = 16,
                    patience: int = 0, time_budget_s: float = 0.0, target_makespan: float = 0.0,
                    heuristic_seeds: bool = True, record_history: bool = False, _no_fused: bool = False):
         """The whole single-GPU search in one C call (sb_search_run).  Returns a dict: opt, prio, makespan, key,

@@ -75,7 +75,7 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
                integer_starts: bool = True, reduced: bool = False, time_budget_s: Optional[float] = None,
                patience: Optional[int] = None, t_start: float = 5e-4, t_end: float = 1e-6,
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
-               target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: int = 4,
+               target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: Optional[int] = None,
                record_history: bool = False, heuristic_seeds: bool = True,
                exchange_every: int = 16, _no_fused: bool = False, _python_driver: bool = False) -> SearchResult:
     """Run the search on `engine` (table already set).  Returns the best candidate found by any rank.
@@ -84,6 +84,8 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     `resample_every` rounds inside a group is only another launch); after each group the ranks exchange
     their best key (one MIN) and the stopping rules are evaluated, so the host synchronises once per
     group rather than once per round."""
+    if resample_every is None:
+        resample_every = -1          # the library's choice: 2 inside the tile kernel, 4 where it costs a copy
     dist = _dist() if use_dist else None
     if dist is None and not reseed_every and not _python_driver and hasattr(engine, "search_run"):
         # one process, one GPU: the same loop runs inside the library (sb_search_run)
@@ -101,7 +103,7 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     t0 = time.perf_counter()
     engine.search_init(chains, seed=seed, chain_base=rank * chains, integer_starts=integer_starts,
                        reduced=reduced, t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1), warm=warm,
-                       **({"_no_fused": True} if _no_fused else {}))
+                       resample_every=resample_every, **({"_no_fused": True} if _no_fused else {}))
     if heuristic_seeds:
         # every rank plants the longest-processing-time seeds in an eighth of its population each;
         # the rest stays random (diversity), tournament resampling then concentrates the population
@@ -147,18 +149,9 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
         history.append((time.perf_counter() - t0, chains * world, key_makespan(key)))
     exchange_every = max(1, int(exchange_every))
     while done_rounds < rounds:
-        # one group: `step` rounds with tournament resampling on its own cadence, no host synchronisation
+        # one group of rounds, no host synchronisation; the library resamples on its own cadence
         step = min(exchange_every, rounds - done_rounds)
-        issued = 0
-        while issued < step:
-            n = step - issued
-            if resample_every:
-                n = min(n, resample_every - ((done_rounds + issued) % resample_every))
-            engine.search_round(n)
-            issued += n
-            at = done_rounds + issued
-            if resample_every and at % resample_every == 0 and at < rounds and issued < step:
-                engine.search_resample()
+        engine.search_round(step)
         done_rounds += step
         r = done_rounds - 1
         key = exchange()
@@ -183,8 +176,6 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
             want_stop = bool(stop.item())
         if want_stop:
             break
-        if resample_every and (r + 1) % resample_every == 0 and r + 1 < rounds:
-            engine.search_resample()
         if reseed_every and (r + 1) % reseed_every == 0 and r + 1 < rounds:
             opt, prio = _gather_best(engine, best_seen, chains, dist, rank)
             engine.search_inject(opt, prio, copies=max(1, chains // 64), first=-1)

@@ -50,7 +50,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = run_search(eng, chains=args.chains, rounds=rounds, seed=0, reduced=True, record_history=True,
-                     exchange_every=args.exchange_every, resample_every=4)
+                     exchange_every=args.exchange_every)
     wall = time.perf_counter() - t0
     if rank == 0:
         print("# %s anneal: J=%d, S=%d (min over strategies), G=1..%d; %d GPU(s) x %d chains x %d rounds\n" % (
