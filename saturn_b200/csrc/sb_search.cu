@@ -3,12 +3,16 @@
 // The reference minimises makespan by branch-and-bound over the MILP of milp.py:96-319 with a
 // wall-clock limit and a warm start (milp.py:103-104,151-155,197-202,323-325).  Here a population
 // of candidates (one per "chain") lives in HBM and each round does, entirely on the device:
-//   propose  : copy the chain's current candidate and apply one move (swap two priorities /
-//              re-insert a job elsewhere in the order / change one job's option);
-//   evaluate : the k_eval_tiles kernel of sb_eval.cu over all proposals (the measured hot path),
-//              folding (makespan, global chain id) into a 64-bit arg-min key;
-//   keep     : if the key improved, save that proposal's encoding as the incumbent;
+//   propose  : apply one move to the chain's current candidate (swap two priorities / re-insert a
+//              job elsewhere in the order / change one job's option / move it to another node);
+//   evaluate : the list-scheduling step of sb_eval.cu (the measured hot path), folding
+//              (makespan, global chain id) into a 64-bit arg-min key;
+//   keep     : if the key improved, save that candidate's encoding as the incumbent;
 //   accept   : Metropolis rule per chain at the round's temperature.
+// Where the rows fit in shared memory all four happen inside k_eval_tiles<..., SEARCH> (sb_eval.cu), up
+// to 8 rounds per launch, tournament resampling included.  This file holds the rest: population
+// initialisation, injection, the copy-kernel form of the tournament, the position-major round kernel
+// for large J (k_search_pos) and the unfused propose / keep / accept kernels (fallback and cross-check).
 // Random numbers are counter-based (seed, global chain id, round), so a run is reproducible and
 // independent of how chains are sharded across GPUs.
 #include "sb_search.h"
