@@ -27,7 +27,9 @@
  *   opt[b][j]    uint8: (s << 3) | (k - 1), k = GPU count of job j's option.
  *   prio[b][i]   uint8 (J <= 256) or uint16: job scheduled i-th; each row is a
  *                permutation of 0..J-1.
- *   rows of opt / prio are `row_stride` ELEMENTS apart (>= J).  Rows that are
+ *   rows of opt / prio are `row_stride` ELEMENTS apart (>= J), and BOTH buffers must span
+ *   B * row_stride elements (the last row included: the aligned paths fetch whole 16- / 32-byte
+ *   chunks of every row, and sb_eval_host copies B * row_stride elements per buffer).  Rows that are
  *   32-byte aligned (base pointers and byte strides multiples of 32) take the
  *   fast path (TMA bulk copies + 256-bit streaming loads); 16-byte aligned rows
  *   use TMA bulk copies only; anything else is fetched with plain loads.
@@ -39,6 +41,12 @@
  *       start = max(ready[sel])
  *       ready[sel] = start + (integer_starts ? ceil(rt) : rt)
  *   makespan = max_j (start_j + rt_j)
+ * With integer_starts the slot state is the integer time a slot becomes usable, start + ceil(rt);
+ * SURVEY.md §8a writes the same rule as `start = ceil(max ready)` over real-valued ready times.  Starts,
+ * makespans and the set of k slots taken are identical (ceil is monotone); the one observable difference
+ * is WHICH of several slots that become free within the same integer second is taken first: here ties are
+ * between equal integer usable-times and go to the lowest slot index.  The oracle (oracle/ref_eval.py)
+ * defines the rule the tests hold the kernels to.
  */
 #ifndef SATURN_B200_H
 #define SATURN_B200_H
@@ -169,6 +177,10 @@ int sb_decode(sb_handle* h, const uint8_t* opt, const void* prio, unsigned flags
  * There is no reference counterpart (the reference solver is a single CPU process). */
 int sb_xchg_create(sb_handle* h, int rank, int world, void* handle_out /* SB_IPC_HANDLE_BYTES */);
 int sb_xchg_connect(sb_handle* h, const void* handles /* [world][SB_IPC_HANDLE_BYTES] */);
+/* One process driving several devices (one handle per device, rank = position in `handles`): the mailboxes
+ * are wired directly — same address space, cudaDeviceEnablePeerAccess, no IPC handles.  Replaces
+ * sb_xchg_create + sb_xchg_connect for that case; the per-round calls are the same. */
+int sb_xchg_connect_local(sb_handle** handles, int n);
 int sb_xchg_post(sb_handle* h, const uint64_t* key_dev);
 /* out_dev receives the MIN over all ranks; fold_dev (nullable) is MIN-ed with it in place */
 int sb_xchg_reduce(sb_handle* h, uint64_t* out_dev, uint64_t* fold_dev);
@@ -249,6 +261,17 @@ int sb_search_seed_lpt(sb_handle* h);
 int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_control* c, const uint8_t* warm_opt,
                   const void* warm_prio, uint8_t* opt_out /*host [J]*/, void* prio_out /*host [J]*/,
                   sb_search_result* result);
+/* The same search sharded over the `n` devices of ONE process (one handle per device, the same table set on
+ * each): the reference calls its solver from a single process (saturn/orchestrator.py:21-23,55,69), so this
+ * is the call that lets that call site use every GPU of the node without torchrun.  Device i runs its own
+ * population of p->chains chains with global ids p->chain_base + i * chains (counter-based RNG: the run is
+ * identical to n single-device processes with those chain bases); after every group of `sync_every` rounds
+ * the devices exchange one uint64 through the NVLink mailboxes (sb_xchg_connect_local is called if the
+ * handles are not wired yet) and the host applies the stopping rules to the folded key.  The winner is read
+ * from the device that owns its chain id.  result->evaluated counts all devices.  n = 1 is sb_search_run. */
+int sb_search_run_multi(sb_handle** handles, int n, const sb_search_params* p, const sb_search_control* c,
+                        const uint8_t* warm_opt, const void* warm_prio, uint8_t* opt_out /*host [J]*/,
+                        void* prio_out /*host [J]*/, sb_search_result* result);
 /* Population size that fills the device exactly once with the round kernel this table gets (resident warps
  * per SM x 32 lanes x SMs).  A population that is a whole multiple of it leaves no partially filled last
  * wave: 131,072 chains on 148 SMs x 12 warps are 2.3 waves and cost 3. */
@@ -260,6 +283,9 @@ int sb_search_wave(sb_handle* h, unsigned flags, int64_t* chains);
  * That layout is internal: every function of this header takes and returns job-indexed opt rows.  All
  * forms are the same Metropolis search; move mixes and RNG streams differ slightly. */
 int sb_search_is_fused(sb_handle* h);
+/* sb_validate on the search population as it stands (every chain's rows: a permutation and existing table
+ * cells), whatever encoding the population is kept in.  Synchronous; bad_rows (host) = offending chains. */
+int sb_search_validate(sb_handle* h, int64_t* bad_rows);
 /* candidates evaluated so far by this handle's searches */
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);
 

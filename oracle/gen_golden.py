@@ -191,7 +191,65 @@ def main_forecast():
     print("wrote", dst, len(out["cases"]), "cases")
 
 
+def _extra_worker(job):
+    """One extra instance in its own process (HiGHS is single-threaded; the pool runs cases side by side)."""
+    name, tuples, timeout = job
+    milp, tight, Strategy, pulp = _load_reference()
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import ref_eval as R
+    rec = run_case(tight, Strategy, pulp, name, tuples, timeout)
+    rec["variant"] = "tight_m"
+    if rec["incumbent"]:
+        plan = R.plan_from_arrays(tuples, rec["sta"], rec["tga"], rec["bss"], rec["bna"])
+        ok, ov, mk = R.check_plan([p[0] for p in plan], [p[1] for p in plan], [p[2] for p in plan],
+                                  [p[3] for p in plan])
+        rec["overlaps"], rec["feasible"] = ov, bool(ok)
+    rec["proven_optimal"] = bool(rec["highs"].get("status") == 0)
+    tab, optmap = R.table_from_tuples(tuples)
+    bf = R.brute_force(tab, optmap, integer_starts=True)
+    rec["bruteforce_int"] = {"makespan": bf[0], "opt": list(bf[1]), "prio": list(bf[2])}
+    bf = R.brute_force(tab, optmap, integer_starts=False)
+    rec["bruteforce_real"] = {"makespan": bf[0], "opt": list(bf[1]), "prio": list(bf[2])}
+    print(name, "status", rec["highs"].get("status"), "mk", rec.get("makespan"), "bf",
+          rec["bruteforce_int"]["makespan"], "overlaps", rec.get("overlaps"), "%.1fs" % rec["solver_wall_s"],
+          flush=True)
+    return rec
+
+
+def main_extra():
+    """Round 2: a thicker pin for SURVEY H6 (the list-schedule candidate space contains a MILP optimum):
+    heterogeneous J = 4..5 instances and J = 6 instances, tight-M reference MILP with long HiGHS limits
+    (run offline, several instances side by side) -> tests/golden/milp_cases_extra.json."""
+    import multiprocessing as mp
+    jobs = []
+    for seed in range(21, 29):
+        jobs.append(("H4_hetero_seed%d" % seed, hetero_tuples(4, seed), 600))
+    for seed in range(31, 39):
+        jobs.append(("H5_hetero_seed%d" % seed, hetero_tuples(5, seed), 900))
+    jobs += [
+        ("J6_g8_seed6", probe_tuples(6, [8], 6), 600),
+        ("J6_g48_seed7", probe_tuples(6, [4, 8], 7), 900),
+        ("J6_g28_seed8", probe_tuples(6, [2, 8], 8), 900),
+        ("H6_hetero_seed41", hetero_tuples(6, 41), 900),
+        ("H6_hetero_seed42", hetero_tuples(6, 42), 900),
+        ("H6_hetero_seed43", hetero_tuples(6, 43), 900),
+        ("J5_g1248_seed9", probe_tuples(5, [1, 2, 4, 8], 9), 900),
+        ("J5_g124_seed10", probe_tuples(5, [1, 2, 4], 10), 900),
+    ]
+    workers = int(os.environ.get("GEN_GOLDEN_WORKERS", "6"))
+    with mp.get_context("spawn").Pool(workers) as pool:
+        recs = pool.map(_extra_worker, jobs, chunksize=1)
+    out = {"generator": "oracle/gen_golden.py --extra", "reference_commit": "b65e3d2",
+           "scipy": __import__("scipy").__version__, "cases": recs}
+    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "milp_cases_extra.json")
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", dst, "proven optimal:", sum(r["proven_optimal"] for r in recs), "of", len(recs))
+
+
 def main():
+    if "--extra" in sys.argv:
+        return main_extra()
     if "--forecast" in sys.argv:
         return main_forecast()
     if "--nodes" in sys.argv:

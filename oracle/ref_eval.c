@@ -37,7 +37,7 @@
     if (nodes < 1 || nodes > NODES_MAX || (nodes > 1 && S != 1)) return -3;                  \
     if (prio_bytes != 1 && prio_bytes != 2) return -2;                                       \
     if (nthreads > 0) {                                                                      \
-      _Pragma("omp parallel for schedule(static) num_threads(nthreads)")                     \
+      _Pragma("omp parallel for schedule(dynamic, 64) num_threads(nthreads)")                \
       for (int64_t b = 0; b < B; ++b) {                                                      \
         NAME##_one(tab, J, S, opt + (size_t)b * J, (const uint8_t*)prio +                    \
                    (size_t)b * J * prio_bytes, prio_bytes, integer_starts, nslot, nodes,     \

@@ -247,11 +247,15 @@ class LpProblem:
         opts = {"disp": False}
         if solver is not None and solver.timeLimit is not None:
             opts["time_limit"] = float(solver.timeLimit)
+        import os as _os
+        if _os.environ.get("ORACLE_MIP_REL_GAP"):      # HiGHS' default relative gap is 1e-4: "optimal" within it
+            opts["mip_rel_gap"] = float(_os.environ["ORACLE_MIP_REL_GAP"])
         res = milp(cvec, constraints=LinearConstraint(A, lo, hi), integrality=integ,
                    bounds=Bounds(lb, ub), options=opts)
         self.status = res.status
         self.info = {"status": int(res.status), "message": str(res.message),
-                     "mip_gap": getattr(res, "mip_gap", None), "n_vars": n,
+                     "mip_gap": getattr(res, "mip_gap", None), "mip_rel_gap_limit": opts.get("mip_rel_gap", 1e-4),
+                     "mip_dual_bound": getattr(res, "mip_dual_bound", None), "n_vars": n,
                      "n_cons": len(self.constraints)}
         LpProblem.last_info = self.info
         if res.x is not None:

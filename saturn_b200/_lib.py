@@ -18,9 +18,9 @@ _FLAG_FORCE_GENERIC = 0x80000000
 SYMBOLS = [
     "sb_abi_version", "sb_last_error", "sb_create", "sb_destroy", "sb_sync", "sb_set_table",
     "sb_set_sentinel", "sb_get_reduced", "sb_eval", "sb_last_eval_path", "sb_validate", "sb_eval_host", "sb_eval_full",
-    "sb_decode", "sb_xchg_create", "sb_xchg_connect", "sb_xchg_post", "sb_xchg_reduce", "sb_xchg_check",
+    "sb_decode", "sb_xchg_create", "sb_xchg_connect", "sb_xchg_connect_local", "sb_xchg_post", "sb_xchg_reduce", "sb_xchg_check",
     "sb_search_init", "sb_search_round", "sb_search_best_key_ptr", "sb_search_best",
-    "sb_search_inject", "sb_search_resample", "sb_search_seed_lpt", "sb_search_run", "sb_search_wave", "sb_search_is_fused", "sb_search_stats",
+    "sb_search_inject", "sb_search_resample", "sb_search_seed_lpt", "sb_search_run", "sb_search_run_multi", "sb_search_wave", "sb_search_is_fused", "sb_search_stats", "sb_search_validate",
 ]
 
 
@@ -78,6 +78,7 @@ def load():
         "sb_decode": [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp],
         "sb_xchg_create": [vp, ci, ci, vp],
         "sb_xchg_connect": [vp, vp],
+        "sb_xchg_connect_local": [C.POINTER(vp), ci],
         "sb_xchg_post": [vp, vp],
         "sb_xchg_reduce": [vp, vp, vp],
         "sb_xchg_check": [vp],
@@ -90,9 +91,12 @@ def load():
         "sb_search_seed_lpt": [vp],
         "sb_search_run": [vp, C.POINTER(SearchParams), C.POINTER(SearchControl), vp, vp, vp, vp,
                           C.POINTER(SearchResultC)],
+        "sb_search_run_multi": [C.POINTER(vp), ci, C.POINTER(SearchParams), C.POINTER(SearchControl), vp, vp, vp, vp,
+                                C.POINTER(SearchResultC)],
         "sb_search_wave": [vp, C.c_uint, C.POINTER(i64)],
         "sb_search_is_fused": [vp],
         "sb_search_stats": [vp, C.POINTER(i64), C.POINTER(i64)],
+        "sb_search_validate": [vp, C.POINTER(i64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

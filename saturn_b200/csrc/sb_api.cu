@@ -525,6 +525,55 @@ int sb_xchg_connect(sb_handle* h, const void* handles) {
   return SB_OK;
 }
 
+int sb_xchg_connect_local(sb_handle** hs, int n) {
+  if (!hs || n < 1 || n > kMaxRanks) return fail(SB_ERR_ARG, "need 1..%d handles", kMaxRanks);
+  for (int i = 0; i < n; ++i) {
+    if (!hs[i]) return fail(SB_ERR_ARG, "handle %d is null", i);
+    for (int j = 0; j < i; ++j)
+      if (hs[j]->dev.ordinal == hs[i]->dev.ordinal)
+        return fail(SB_ERR_ARG, "handles %d and %d share device %d; one handle per device", j, i, hs[i]->dev.ordinal);
+  }
+  // every handle gets a fresh mailbox on its own device
+  for (int i = 0; i < n; ++i) {
+    sb_handle* h = hs[i];
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    free_xchg(h);
+    const size_t bytes = 2 * kMaxRanks * 2 * sizeof(unsigned long long);
+    CK(cudaMalloc(&h->xd.local, bytes));
+    CK(cudaMemset(h->xd.local, 0, bytes));
+    CK(cudaMalloc(&h->d_xcounter, sizeof(unsigned)));
+    CK(cudaMemset(h->d_xcounter, 0, sizeof(unsigned)));
+    CK(cudaMalloc(&h->d_xerr, sizeof(int)));
+    CK(cudaMemset(h->d_xerr, 0, sizeof(int)));
+    h->xd.rank = i;
+    h->xd.world = n;
+    h->xchg_created = true;
+  }
+  // same address space: a peer's mailbox is reachable as soon as peer access is on (no IPC handles)
+  for (int i = 0; i < n; ++i) {
+    sb_handle* h = hs[i];
+    CK(cudaSetDevice(h->dev.ordinal));
+    for (int j = 0; j < n; ++j) {
+      if (j != i) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, h->dev.ordinal, hs[j]->dev.ordinal));
+        if (!can)
+          return fail(SB_ERR_UNSUPPORTED, "device %d cannot map device %d's memory (no NVLink / P2P path)",
+                      h->dev.ordinal, hs[j]->dev.ordinal);
+        cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->dev.ordinal, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return fail(SB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", h->dev.ordinal,
+                                               hs[j]->dev.ordinal, cudaGetErrorString(e));
+      }
+      h->xd.peer[j] = hs[j]->xd.local;
+    }
+    h->xchg_ready = true;
+  }
+  return SB_OK;
+}
+
 int sb_xchg_post(sb_handle* h, const uint64_t* key_dev) {
   int rc = use_device(h);
   if (rc) return rc;
@@ -661,8 +710,7 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   }
   CK(cudaMemsetAsync(s.tail_counter, 0, sizeof(unsigned), h->stream));
   CK(cudaMemsetAsync(d.keys, 0xff, 2 * sizeof(unsigned long long), h->stream));
-  CK(cudaMemsetAsync(d.cur_o, 0, P * d.stride_o, h->stream));
-  CK(cudaMemsetAsync(d.cur_p, 0, P * d.stride_p, h->stream));
+  // (the initialisation kernels write whole rows, padding included: no memset of the population)
   // Rows that do not fit in shared memory: keep the population in schedule order and stream both rows.
   const int SGs = (reduced ? 1 : h->S) * kSlots;
   const bool no_fused = (p->flags & 0x20000000u) != 0;  // test hook
@@ -932,46 +980,117 @@ int sb_search_seed_lpt(sb_handle* h) {
   return SB_OK;
 }
 
-int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_control* c, const uint8_t* warm_opt,
-                  const void* warm_prio, uint8_t* opt_out, void* prio_out, sb_search_result* result) {
-  if (!h || !p || !c) return fail(SB_ERR_ARG, "null argument");
+// The search loop shared by sb_search_run (n = 1) and sb_search_run_multi (one handle per device of this
+// process): every device runs its own population; after each group of rounds the devices exchange ONE uint64
+// over NVLink peer memory (publish in the own mailbox, fold of all mailboxes by a one-warp kernel), the host
+// reads the folded key of every device with one copy each and applies the stopping rules.
+static int search_run_impl(sb_handle** hs, int n, const sb_search_params* p, const sb_search_control* c,
+                           const uint8_t* warm_opt, const void* warm_prio, uint8_t* opt_out, void* prio_out,
+                           sb_search_result* result) {
+  if (!hs || !p || !c) return fail(SB_ERR_ARG, "null argument");
+  if (n < 1 || n > kMaxRanks) return fail(SB_ERR_ARG, "need 1..%d handles", kMaxRanks);
   if (c->rounds < 1 || c->sync_every < 1 || c->resample_every < -1 || c->patience < 0)
     return fail(SB_ERR_ARG, "rounds / sync_every must be >= 1, resample_every >= -1, patience >= 0");
+  for (int i = 0; i < n; ++i)
+    if (!hs[i]) return fail(SB_ERR_ARG, "handle %d is null", i);
   const auto t0 = std::chrono::steady_clock::now();
   auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
-  sb_search_params pp = *p;
-  pp.total_rounds = c->rounds;
-  pp.resample_every = c->resample_every;
-  int rc = sb_search_init(h, &pp, warm_opt, warm_prio);
-  if (rc) return rc;
-  if (c->heuristic_seeds && (rc = sb_search_seed_lpt(h))) return rc;
-  SearchState& s = h->search;
-  int hist = 0;
-  auto read_key = [&](unsigned long long* key) -> int {
-    CK(cudaMemcpyAsync(key, s.d.keys + 1, sizeof(*key), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+  int rc;
+  if (n > 1) {
+    bool wired = true;
+    for (int i = 0; i < n; ++i) wired = wired && hs[i]->xchg_ready && hs[i]->xd.world == n && hs[i]->xd.rank == i;
+    if (!wired && (rc = sb_xchg_connect_local(hs, n))) return rc;
+  }
+  for (int i = 0; i < n; ++i) {
+    sb_search_params pp = *p;
+    pp.total_rounds = c->rounds;
+    pp.resample_every = c->resample_every;
+    pp.chain_base = p->chain_base + static_cast<uint64_t>(i) * static_cast<uint64_t>(p->chains);
+    // the warm start goes to device 0 only: one copy of the previous plan is enough, the rest stays diverse
+    if ((rc = sb_search_init(hs[i], &pp, i == 0 ? warm_opt : nullptr, i == 0 ? warm_prio : nullptr))) return rc;
+    if (c->heuristic_seeds && (rc = sb_search_seed_lpt(hs[i]))) return rc;
+  }
+  std::vector<unsigned long long> hk(n, ~0ull);
+  std::vector<int> herr(n, 0);
+  // one exchange + host read: returns the best key over all devices
+  auto exchange = [&](unsigned long long* best) -> int {
+    if (n == 1) {
+      sb_handle* h = hs[0];
+      CK(cudaSetDevice(h->dev.ordinal));
+      CK(cudaMemcpyAsync(&hk[0], h->search.d.keys + 1, sizeof(hk[0]), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      *best = hk[0];
+      return SB_OK;
+    }
+    for (int i = 0; i < n; ++i) {
+      sb_handle* h = hs[i];
+      CK(cudaSetDevice(h->dev.ordinal));
+      ++h->xseq;
+      CK(xchg_post_launch(h->xd, h->search.d.keys + 1, h->xseq, h->stream));  // the key of the SAVED encoding
+    }
+    for (int i = 0; i < n; ++i) {
+      sb_handle* h = hs[i];
+      CK(cudaSetDevice(h->dev.ordinal));
+      CK(cudaMemsetAsync(h->d_scratch + 2, 0xff, sizeof(unsigned long long), h->stream));  // a timed-out fold leaves ~0
+      CK(xchg_reduce_launch(h->xd, h->xseq, h->d_scratch + 2, nullptr, h->d_xerr, h->stream));
+      CK(cudaMemcpyAsync(&hk[i], h->d_scratch + 2, sizeof(hk[i]), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(&herr[i], h->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    for (int i = 0; i < n; ++i) {
+      CK(cudaSetDevice(hs[i]->dev.ordinal));
+      CK(cudaStreamSynchronize(hs[i]->stream));
+    }
+    for (int i = 0; i < n; ++i) {
+      if (herr[i]) return fail(SB_ERR_CUDA, "peer exchange timed out on device %d waiting for a device's key", hs[i]->dev.ordinal);
+      if (hk[i] != hk[0]) return fail(SB_ERR_CUDA, "devices disagree on the folded key (%llx on %d, %llx on %d)", hk[0],
+                                      hs[0]->dev.ordinal, hk[i], hs[i]->dev.ordinal);
+    }
+    *best = hk[0];
     return SB_OK;
   };
+  auto evaluated = [&]() {
+    long long e = 0;
+    for (int i = 0; i < n; ++i) e += hs[i]->search.evaluated;
+    return e;
+  };
+  int hist = 0;
   auto record = [&](unsigned long long key) {
     if (c->history_cap > 0 && hist < c->history_cap) {
       uint32_t bits = static_cast<uint32_t>(key >> 32);
       float mk;
       memcpy(&mk, &bits, 4);
       if (c->history_wall_s) c->history_wall_s[hist] = elapsed();
-      if (c->history_evaluated) c->history_evaluated[hist] = s.evaluated;
+      if (c->history_evaluated) c->history_evaluated[hist] = evaluated();
       if (c->history_makespan) c->history_makespan[hist] = mk;
       ++hist;
     }
   };
+  if (n > 1) {
+    // every device has finished its initialisation (first launches load their kernels) before the first
+    // bounded wait on a peer's mailbox
+    for (int i = 0; i < n; ++i) {
+      CK(cudaSetDevice(hs[i]->dev.ordinal));
+      CK(cudaStreamSynchronize(hs[i]->stream));
+    }
+  }
   unsigned long long best = 0, key = 0;
-  if ((rc = read_key(&best))) return rc;
+  if ((rc = exchange(&best))) return rc;
   record(best);
   int done = 0, stale = 0, reason = 0;
+  bool first_group = true;
   while (done < c->rounds) {
     const int step = std::min(c->sync_every, c->rounds - done);
-    if ((rc = sb_search_round(h, step))) return rc;  // resamples on its own cadence (sb_search_params)
+    for (int i = 0; i < n; ++i)
+      if ((rc = sb_search_round(hs[i], step))) return rc;  // asynchronous; resamples on its own cadence
+    if (n > 1 && first_group) {
+      for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(hs[i]->dev.ordinal));
+        CK(cudaStreamSynchronize(hs[i]->stream));
+      }
+      first_group = false;
+    }
     done += step;
-    if ((rc = read_key(&key))) return rc;
+    if ((rc = exchange(&key))) return rc;
     if (key < best) { best = key; stale = 0; } else { stale += step; }
     record(best);
     uint32_t bits = static_cast<uint32_t>(best >> 32);
@@ -981,19 +1100,43 @@ int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_contr
     if (c->patience > 0 && stale >= c->patience) { reason = 2; break; }
     if (c->target_makespan > 0 && mk <= c->target_makespan) { reason = 3; break; }
   }
+  // the incumbent lives on the device that owns the chain id in the key
+  int owner = 0;
+  if (n > 1) {
+    const uint64_t id = best & 0xffffffffull;
+    const uint64_t rel = (id - (p->chain_base & 0xffffffffull)) & 0xffffffffull;
+    owner = static_cast<int>(rel / static_cast<uint64_t>(p->chains));
+    if (owner >= n) return fail(SB_ERR_STATE, "best key %llx names chain %llu outside the %d populations", best,
+                                static_cast<unsigned long long>(rel), n);
+  }
   float mk = 0.f;
   uint64_t k64 = 0;
-  if ((rc = sb_search_best(h, opt_out, prio_out, &mk, &k64))) return rc;
+  if ((rc = sb_search_best(hs[owner], opt_out, prio_out, &mk, &k64))) return rc;
+  if (n > 1 && k64 != best)
+    return fail(SB_ERR_STATE, "device %d saved key %llx, the exchange says %llx", hs[owner]->dev.ordinal,
+                static_cast<unsigned long long>(k64), best);
   if (c->history_len) *c->history_len = hist;
   if (result) {
     result->makespan = mk;
     result->key = k64;
-    result->evaluated = s.evaluated;
+    result->evaluated = evaluated();
     result->rounds = done;
     result->stop_reason = reason;
     result->wall_s = elapsed();
   }
   return SB_OK;
+}
+
+int sb_search_run(sb_handle* h, const sb_search_params* p, const sb_search_control* c, const uint8_t* warm_opt,
+                  const void* warm_prio, uint8_t* opt_out, void* prio_out, sb_search_result* result) {
+  if (!h) return fail(SB_ERR_ARG, "null argument");
+  return search_run_impl(&h, 1, p, c, warm_opt, warm_prio, opt_out, prio_out, result);
+}
+
+int sb_search_run_multi(sb_handle** handles, int n, const sb_search_params* p, const sb_search_control* c,
+                        const uint8_t* warm_opt, const void* warm_prio, uint8_t* opt_out, void* prio_out,
+                        sb_search_result* result) {
+  return search_run_impl(handles, n, p, c, warm_opt, warm_prio, opt_out, prio_out, result);
 }
 
 int sb_search_wave(sb_handle* h, unsigned flags, int64_t* chains) {
@@ -1014,6 +1157,24 @@ int sb_search_wave(sb_handle* h, unsigned flags, int64_t* chains) {
     if (warps < 1) warps = 4;
   }
   *chains = static_cast<int64_t>(warps) * 32 * h->dev.sm_count;
+  return SB_OK;
+}
+
+int sb_search_validate(sb_handle* h, int64_t* bad_rows) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  if (!bad_rows) return fail(SB_ERR_ARG, "bad_rows is null");
+  EvalCall c;
+  if ((rc = make_call(h, s.d.cur_o, s.d.cur_p, s.d.chains, s.d.stride_o, s.p.flags & (SB_FLAG_REDUCED | SB_FLAG_INTEGER_STARTS), &c)))
+    return rc;
+  CK(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long), h->stream));
+  CK(validate_launch(h->dev, c, h->d_scratch, h->stream, s.d.pos != 0));
+  unsigned long long bad = 0;
+  CK(cudaMemcpyAsync(&bad, h->d_scratch, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *bad_rows = static_cast<int64_t>(bad);
   return SB_OK;
 }
 

@@ -96,10 +96,13 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
   st.orow = tile_o + lane * a.row_o;
   st.ns = node_s + lane;
 
-  if (a.xp.counter != nullptr && a.xp.fold_prev && a.xp.seq > 1 && blockIdx.x == 0 && warp == 0) {
-    // pipelined exchange, prologue: fold the keys every rank published for the PREVIOUS round
-    // (lane r loads rank r's mailbox over NVLink, acquire at system scope) into best_key.  The 0.45 ms
-    // of evaluation that follows hides the NVLink latency; the publish of this round is in the tail.
+  // Pipelined exchange: warp 0 of CTA 0 folds the keys every rank published for the PREVIOUS round into
+  // best_key (lane r loads rank r's mailbox over NVLink, acquire at system scope).  It never blocks in front
+  // of its tiles: it looks once here and then once per tile boundary until every rank's round has shown up
+  // (a late peer costs this warp one NVLink round trip per look instead of stalling the CTA's slowest
+  // warp), and only spins — bounded — after its last tile.  The publish of this round is in the tail.
+  bool fold_pending = a.xp.counter != nullptr && a.xp.fold_prev && a.xp.seq > 1 && blockIdx.x == 0 && warp == 0;
+  auto try_fold = [&](bool block) {
     const unsigned long long want = a.xp.seq - 1;
     unsigned long long k = ~0ull;
     bool ok = true;
@@ -107,31 +110,35 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       const unsigned long long* slot = a.xp.x.peer[lane] + (want & 1ull) * 2;
       unsigned long long seen;
       unsigned spins = 0;
-      do {
+      for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(slot + 1) : "memory");
-        if (seen >= want) break;
+        if (seen >= want || !block || ++spins >= (1u << 22)) break;
         __nanosleep(64);
-      } while (++spins < (1u << 22));
+      }
       ok = seen >= want;
       if (ok) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(k) : "l"(slot) : "memory");
     }
     ok = __all_sync(0xffffffffu, ok);
+    if (!ok) {
+      if (block && lane == 0) *a.xp.error = 1;  // a peer never published: report, do not hang
+      return;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, d);
       k = o < k ? o : k;
     }
-    if (lane == 0) {
-      if (!ok) *a.xp.error = 1;
-      else atomicMin(a.best_key, k);
-    }
-  }
+    if (lane == 0) atomicMin(a.best_key, k);
+    fold_pending = false;
+  };
+  if (fold_pending) try_fold(false);
 
   uint32_t phase = 0;
   bool tab_ready = TABG;
   for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
        tile += static_cast<long long>(gridDim.x) * nw) {
     const long long b0 = tile * 32;
+    if (!SEARCH && fold_pending) try_fold(false);
     // the candidate of this lane: consecutive ids, or (search rounds, sf.deal = 1) one id from each of 32
     // far-apart blocks so that successive launches put different chains into one warp
     const long long cand = (SEARCH && a.sf.deal) ? lane * a.ntiles + tile : b0 + lane;
@@ -293,6 +300,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
     }
   }
   if (!tab_ready && threadIdx.x == 0) mbar_wait(bar_tab, 0);  // never leave a bulk copy in flight
+  if (!SEARCH && fold_pending) try_fold(true);  // before the tail: the publish of this round follows the fold
   if (SEARCH) {
     if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
     return;
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(128) k_eval_full(const FullArgs a) {
 // names an existing (finite) table cell (and, with several nodes, an existing node).
 // bad[0] counts offending rows.
 __global__ void k_validate(const float* tab, int J, int SG, int nodes, const uint8_t* opt, const uint8_t* prio, int pb,
-                           long long B, long long stride_o, long long stride_p, unsigned long long* bad) {
+                           long long B, long long stride_o, long long stride_p, unsigned long long* bad, int by_pos) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -477,12 +485,13 @@ __global__ void k_validate(const float* tab, int J, int SG, int nodes, const uin
         const uint32_t old = atomicOr(&seen[j >> 5], 1u << (j & 31));
         if (old & (1u << (j & 31))) ok = false;
       }
-      int o = orow[i];
+      int o = orow[i];  // the option of job i — or, by_pos, of the job scheduled i-th
       if (nodes > 1) {
         if ((o >> 3) >= nodes) ok = false;
         o &= 7;
       }
-      if (o >= SG || !isfinite(tab[static_cast<size_t>(i) * SG + o])) ok = false;
+      const int job = by_pos ? (j < J ? j : 0) : i;
+      if (o >= SG || !isfinite(tab[static_cast<size_t>(job) * SG + o])) ok = false;
     }
     ok = __all_sync(0xffffffffu, ok);
     if (!ok && lane == 0) atomicAdd(bad, 1ull);
@@ -687,7 +696,7 @@ cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start,
   return cudaGetLastError();
 }
 
-cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st) {
+cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st, bool by_pos) {
   if (c.B <= 0) return cudaSuccess;
   const int pb = c.J <= 256 ? 1 : 2;
   const int words = (c.J + 31) / 32;
@@ -696,7 +705,8 @@ cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long 
   long long blocks = (c.B + 3) / 4;
   long long cap = static_cast<long long>(dev.sm_count) * 8;
   int grid = static_cast<int>(blocks < cap ? blocks : cap);
-  k_validate<<<grid, threads, smem, st>>>(c.tab, c.J, c.SG, c.nodes, c.opt, c.prio, pb, c.B, c.stride_o, c.stride_p, bad);
+  k_validate<<<grid, threads, smem, st>>>(c.tab, c.J, c.SG, c.nodes, c.opt, c.prio, pb, c.B, c.stride_o, c.stride_p, bad,
+                                          by_pos ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -86,7 +86,8 @@ cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, i
 int search_round_mode(const Device& dev, int J, int SG, int nodes);
 cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st);
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st);
-cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st);
+cudaError_t validate_launch(const Device& dev, const EvalCall& c, unsigned long long* bad, cudaStream_t st,
+                            bool by_pos = false);
 
 // table construction (sb_table.cu)
 cudaError_t build_table_launch(const float* T, int J, int S, int G, uint64_t gcount_packed, float* tab, float* tmin,

@@ -53,7 +53,7 @@ __global__ void k_xchg_reduce(XchgDev x, unsigned long long seq, unsigned long l
     const unsigned long long* slot = x.peer[r] + (seq & 1ull) * 2;
     unsigned spins = 0;
     while (ld_acquire_sys(slot + 1) < seq) {
-      if (++spins > (1u << 22)) {  // ~0.1-0.5 s: a peer died or never posted; report, do not hang
+      if (++spins > (1u << 22)) {  // seconds (each look is an NVLink round trip): a peer died or never posted
         ok = false;
         break;
       }
@@ -70,6 +70,7 @@ __global__ void k_xchg_reduce(XchgDev x, unsigned long long seq, unsigned long l
   if (threadIdx.x == 0) {
     if (!all_ok) {
       *error = 1;
+      *out = ~0ull;  // never leave a stale key behind a timed-out wait
     } else {
       *out = k;
       if (fold != nullptr && k < *fold) *fold = k;

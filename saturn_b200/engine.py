@@ -197,15 +197,21 @@ class Engine:
         cannot be opened."""
         rank, world = dist.get_rank(), dist.get_world_size()
         hdl = np.zeros(_lib.IPC_HANDLE_BYTES, dtype=np.uint8)
-        check(self._lib.sb_xchg_create(self._h, rank, world, C.c_void_p(hdl.ctypes.data)))
+        # success or failure is decided COLLECTIVELY: a rank whose local step fails still takes part in the
+        # all_gather / all_reduce below, so no rank is left waiting in a collective and all ranks end up
+        # with the same answer (some posting to mailboxes while others call NCCL would deadlock)
+        ok_local = self._lib.sb_xchg_create(self._h, rank, world, C.c_void_p(hdl.ctypes.data)) == 0
         mine = torch.from_numpy(hdl).to(self.device)
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
-        flat = torch.stack(allh).cpu().numpy().copy()
-        rc = self._lib.sb_xchg_connect(self._h, C.c_void_p(flat.ctypes.data))
-        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)           # all ranks or none
-        self._xchg = bool(ok.item())
+        okt = torch.tensor([1 if ok_local else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)           # every rank created its mailbox?
+        if bool(okt.item()):
+            flat = torch.stack(allh).cpu().numpy().copy()
+            ok_local = self._lib.sb_xchg_connect(self._h, C.c_void_p(flat.ctypes.data)) == 0
+            okt.fill_(1 if ok_local else 0)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)       # every rank mapped every peer?
+        self._xchg = bool(okt.item())
         return self._xchg
 
     @property
@@ -255,35 +261,9 @@ class Engine:
                    heuristic_seeds: bool = True, record_history: bool = False, _no_fused: bool = False):
         """The whole single-GPU search in one C call (sb_search_run).  Returns a dict: opt, prio, makespan, key,
         evaluated, rounds, stop_reason, wall_s, history [(wall s, evaluated, makespan)]."""
-        J = self.J
-        pdt = np.uint8 if J <= 256 else np.uint16
-        p = SearchParams(seed=seed, chains=chains, chain_base=chain_base,
-                         flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
-                         t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1))
-        cap = (max(rounds, 1) // max(1, sync_every) + 3) if record_history else 0
-        hw, he, hm = np.zeros(cap, np.float64), np.zeros(cap, np.int64), np.zeros(cap, np.float32)
-        hl = C.c_int(0)
-        ctl = _lib.SearchControl(rounds=max(rounds, 1), resample_every=int(resample_every), sync_every=max(1, int(sync_every)),
-                                 patience=int(patience or 0), heuristic_seeds=1 if heuristic_seeds else 0,
-                                 target_makespan=float(target_makespan or 0.0), time_budget_s=float(time_budget_s or 0.0),
-                                 history_cap=cap, history_len=C.pointer(hl),
-                                 history_wall_s=hw.ctypes.data_as(C.POINTER(C.c_double)),
-                                 history_evaluated=he.ctypes.data_as(C.POINTER(C.c_int64)),
-                                 history_makespan=hm.ctypes.data_as(C.POINTER(C.c_float)))
-        wo = wp = None
-        keep = None
-        if warm is not None:
-            keep = (np.ascontiguousarray(warm[0], dtype=np.uint8), np.ascontiguousarray(warm[1], dtype=pdt))
-            wo, wp = C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data)
-        opt, prio = np.empty(J, dtype=np.uint8), np.empty(J, dtype=pdt)
-        res = _lib.SearchResultC()
-        check(self._lib.sb_search_run(self._h, C.byref(p), C.byref(ctl), wo, wp, C.c_void_p(opt.ctypes.data),
-                                      C.c_void_p(prio.ctypes.data), C.byref(res)))
-        del keep
-        n = int(hl.value)
-        return {"opt": opt, "prio": prio, "makespan": float(res.makespan), "key": int(res.key),
-                "evaluated": int(res.evaluated), "rounds": int(res.rounds), "stop_reason": int(res.stop_reason),
-                "wall_s": float(res.wall_s), "history": [(float(hw[i]), int(he[i]), float(hm[i])) for i in range(n)]}
+        return _search_run(self._lib, [self._h], self.J, chains, rounds, seed, chain_base, integer_starts, reduced,
+                           t_start, t_end, warm, resample_every, sync_every, patience, time_budget_s, target_makespan,
+                           heuristic_seeds, record_history, _no_fused)
 
     def search_wave(self, reduced: bool = False) -> int:
         """Chains that fill the device exactly once with the round kernel of the current table; populations
@@ -323,10 +303,112 @@ class Engine:
     def search_resample(self):
         check(self._lib.sb_search_resample(self._h))
 
+    def search_validate(self) -> int:
+        """Chains of the current population whose rows are not a permutation + existing table cells."""
+        bad = C.c_int64(0)
+        check(self._lib.sb_search_validate(self._h, C.byref(bad)))
+        return int(bad.value)
+
     def search_stats(self):
         ev, rd = C.c_int64(0), C.c_int64(0)
         check(self._lib.sb_search_stats(self._h, C.byref(ev), C.byref(rd)))
         return int(ev.value), int(rd.value)
+
+
+def _search_run(lib, handles, J, chains, rounds, seed, chain_base, integer_starts, reduced, t_start, t_end, warm,
+                resample_every, sync_every, patience, time_budget_s, target_makespan, heuristic_seeds,
+                record_history, _no_fused):
+    """sb_search_run (one handle) / sb_search_run_multi (one handle per device of this process)."""
+    pdt = np.uint8 if J <= 256 else np.uint16
+    p = SearchParams(seed=seed, chains=chains, chain_base=chain_base,
+                     flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
+                     t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1))
+    cap = (max(rounds, 1) // max(1, sync_every) + 3) if record_history else 0
+    hw, he, hm = np.zeros(cap, np.float64), np.zeros(cap, np.int64), np.zeros(cap, np.float32)
+    hl = C.c_int(0)
+    ctl = _lib.SearchControl(rounds=max(rounds, 1), resample_every=int(resample_every), sync_every=max(1, int(sync_every)),
+                             patience=int(patience or 0), heuristic_seeds=1 if heuristic_seeds else 0,
+                             target_makespan=float(target_makespan or 0.0), time_budget_s=float(time_budget_s or 0.0),
+                             history_cap=cap, history_len=C.pointer(hl),
+                             history_wall_s=hw.ctypes.data_as(C.POINTER(C.c_double)),
+                             history_evaluated=he.ctypes.data_as(C.POINTER(C.c_int64)),
+                             history_makespan=hm.ctypes.data_as(C.POINTER(C.c_float)))
+    wo = wp = None
+    keep = None
+    if warm is not None:
+        keep = (np.ascontiguousarray(warm[0], dtype=np.uint8), np.ascontiguousarray(warm[1], dtype=pdt))
+        wo, wp = C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data)
+    opt, prio = np.empty(J, dtype=np.uint8), np.empty(J, dtype=pdt)
+    res = _lib.SearchResultC()
+    if len(handles) == 1:
+        check(lib.sb_search_run(handles[0], C.byref(p), C.byref(ctl), wo, wp, C.c_void_p(opt.ctypes.data),
+                                C.c_void_p(prio.ctypes.data), C.byref(res)))
+    else:
+        arr = (C.c_void_p * len(handles))(*[h.value for h in handles])
+        check(lib.sb_search_run_multi(arr, len(handles), C.byref(p), C.byref(ctl), wo, wp,
+                                      C.c_void_p(opt.ctypes.data), C.c_void_p(prio.ctypes.data), C.byref(res)))
+    del keep
+    n = int(hl.value)
+    return {"opt": opt, "prio": prio, "makespan": float(res.makespan), "key": int(res.key),
+            "evaluated": int(res.evaluated), "rounds": int(res.rounds), "stop_reason": int(res.stop_reason),
+            "wall_s": float(res.wall_s), "history": [(float(hw[i]), int(he[i]), float(hm[i])) for i in range(n)]}
+
+
+class MultiEngine:
+    """N handles on N devices of THIS process behind the interface `saturn.solver.solve` uses: the table is
+    replicated, the search population is sharded by global chain id (sb_search_run_multi: one MIN of a uint64
+    per group of rounds over NVLink peer memory, no torchrun, no NCCL), the winner is decoded on the first
+    device.  The reference calls its solver from one process (saturn/orchestrator.py:21-23,55,69); this is how
+    that call site reaches every GPU of the node."""
+
+    def __init__(self, devices):
+        if isinstance(devices, int):
+            devices = list(range(devices))
+        devices = [int(d) for d in devices]
+        if len(devices) < 1:
+            raise ValueError("need at least one device")
+        if len(set(devices)) != len(devices):
+            raise ValueError("devices must be distinct")
+        self.engines = [Engine(d, stream=torch.cuda.current_stream(torch.device("cuda", d))) for d in devices]
+        self._lib = self.engines[0]._lib
+        self.device = self.engines[0].device
+        self.devices = devices
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def set_table(self, T, gcount=None, sentinel=None, nodes: int = 1):
+        for e in self.engines:
+            e.set_table(T, gcount, sentinel=sentinel, nodes=nodes)
+        return self
+
+    J = property(lambda self: self.engines[0].J)
+    S = property(lambda self: self.engines[0].S)
+    G = property(lambda self: self.engines[0].G)
+    gcount = property(lambda self: self.engines[0].gcount)
+    nodes = property(lambda self: self.engines[0].nodes)
+    prio_dtype = property(lambda self: self.engines[0].prio_dtype)
+
+    def reduced_table(self):
+        return self.engines[0].reduced_table()
+
+    def decode(self, *a, **kw):
+        return self.engines[0].decode(*a, **kw)
+
+    def search_wave(self, reduced: bool = False) -> int:
+        """chains PER DEVICE that fill one device exactly once."""
+        return self.engines[0].search_wave(reduced)
+
+    def search_run(self, chains: int, rounds: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
+                   reduced: bool = False, t_start: float = 5e-4, t_end: float = 1e-6, warm=None,
+                   resample_every: int = -1, sync_every: int = 16, patience: int = 0, time_budget_s: float = 0.0,
+                   target_makespan: float = 0.0, heuristic_seeds: bool = True, record_history: bool = False,
+                   _no_fused: bool = False):
+        """`chains` is per device; the result's `evaluated` counts every device."""
+        return _search_run(self._lib, [e._h for e in self.engines], self.J, chains, rounds, seed, chain_base,
+                           integer_starts, reduced, t_start, t_end, warm, resample_every, sync_every, patience,
+                           time_budget_s, target_makespan, heuristic_seeds, record_history, _no_fused)
 
 
 class _CudaArrayView:

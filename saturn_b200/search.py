@@ -115,7 +115,8 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
             first = min(i * per, max(0, chains - per))
             engine.search_inject(opt.astype(np.uint8), order.astype(pdt), copies=min(per, chains), first=first)
     local_key = engine.search_best_key()          # aliases device memory
-    gkey = torch.empty(1, dtype=torch.int64, device=engine.device)
+    KEY_MAX = 0x7fffffffffffffff
+    gkey = torch.full((1,), KEY_MAX, dtype=torch.int64, device=engine.device)
     history: List[Tuple[float, int, float]] = []
     best_seen = None
     stale = 0
@@ -124,19 +125,22 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
 
     if dist and not getattr(engine, "has_xchg", False) and hasattr(engine, "xchg_init") \
             and dist.get_backend() == "nccl":
-        try:
-            engine.xchg_init(dist)          # NVLink peer-memory mailboxes; stays on NCCL if it cannot map peers
-        except Exception:
-            pass
+        engine.xchg_init(dist)              # NVLink peer-memory mailboxes; collectively False -> NCCL on all ranks
     use_xchg = bool(dist) and getattr(engine, "has_xchg", False)
 
     def exchange() -> int:
         if use_xchg:
-            # NVLink peer-memory MIN: every rank stores its key into every peer's mailbox
+            # NVLink peer-memory MIN: every rank publishes its key in its own mailbox, a one-warp kernel
+            # folds all mailboxes.  A wait that times out (a peer seconds late: a dead rank) leaves the
+            # preset maximum in gkey and raises here — a loud failure, never a stale key as the owner id.
+            gkey.fill_(KEY_MAX)
             engine.xchg_post(local_key)
             engine.xchg_reduce(gkey)
-            engine.sync()
-            return int(gkey.item())
+            engine.xchg_check()             # synchronises; raises SaturnB200Error on a timed-out wait
+            k = int(gkey.item())
+            if k == KEY_MAX:
+                raise RuntimeError("peer exchange produced no key")
+            return k
         engine.sync()
         gkey.copy_(local_key)
         if dist:

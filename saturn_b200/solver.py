@@ -162,15 +162,44 @@ def candidate_from_arrays(task_list, presolved, nodes: int = 1):
 
 # ------------------------------------------------------------------------------------------ solve
 _ENGINE = None
+_MULTI: dict = {}
 last_stats: dict = {}
+FP32_EXACT_HORIZON = float(1 << 24)   # integer seconds are exact in the kernels' fp32 state below this
 
 
-def _engine():
+def _engine(devices=None):
+    """The process-wide engine: one device (default), or — `devices` = N or a list of ordinals, else
+    SATURN_B200_DEVICES — one handle per device of this process (engine.MultiEngine)."""
     global _ENGINE
-    if _ENGINE is None:
-        from .engine import Engine
-        _ENGINE = Engine()
-    return _ENGINE
+    if devices is None:
+        env = os.environ.get("SATURN_B200_DEVICES", "")
+        if env:
+            devices = [int(x) for x in env.split(",")] if "," in env else int(env)
+    if devices is not None and not isinstance(devices, int):
+        devices = tuple(int(d) for d in devices)
+        if len(devices) == 1:
+            devices = None if devices[0] == 0 else devices
+    if devices is None or devices == 1:
+        if _ENGINE is None:
+            from .engine import Engine
+            _ENGINE = Engine()
+        return _ENGINE
+    if devices not in _MULTI:
+        from .engine import MultiEngine
+        _MULTI[devices] = MultiEngine(devices)
+    return _MULTI[devices]
+
+
+def _check_horizon(T):
+    """The kernels keep schedule times in fp32: `start + ceil(rt)` is exact only below 2^24 s (194 days).
+    A table whose worst-case serial schedule can cross that bound would silently lose the integer-start and
+    no-overlap properties of the emitted plan, so it is refused here (rescale to coarser time units)."""
+    finite = np.where(np.isfinite(T), T, 0.0).astype(np.float64)
+    horizon = float(np.ceil(finite.reshape(T.shape[0], -1).max(axis=1)).sum())
+    if horizon >= FP32_EXACT_HORIZON:
+        raise SolverError("sum of the tasks' longest runtimes is %.3g s >= 2^24 s: schedule times are not exact in "
+                          "fp32 at that horizon; express runtimes in coarser units (e.g. minutes) or drop sentinel "
+                          "options" % horizon)
 
 
 def _default_nodes() -> int:
@@ -189,13 +218,18 @@ def _default_nodes() -> int:
 def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count() or 4) // 4), interval=1000,
           timeout=500, *, chains: Optional[int] = None, rounds: Optional[int] = None, seed: int = 0,
           integer_starts: bool = True, engine=None, hysteresis: Optional[bool] = None,
-          nodes: Optional[int] = None):
+          nodes: Optional[int] = None, devices=None):
     """Drop-in for saturn.solver.solve (milp.py:23).
 
     Returns (sta, tga, bss, bna, boa, makespan) — milp.py:445 — with a real float makespan
     (the reference returns None on a cold start, milp.py:394-399; callers only thread it back in
     as `presolved`).  Keyword-only extras tune the GPU search; environment overrides:
     SATURN_B200_CHAINS, SATURN_B200_ROUNDS, SATURN_B200_BUDGET_S, SATURN_B200_HYSTERESIS.
+
+    Devices.  `devices=N` (or a list of CUDA ordinals, or SATURN_B200_DEVICES) shards the search population
+    over N GPUs of this process — one handle per device, one MIN of a uint64 per group of rounds over NVLink
+    peer memory (sb_search_run_multi); `chains` is per device.  The reference calls solve() from a single
+    process (orchestrator.py:21-23,55,69), so this is how that call site uses the whole node.
 
     Nodes.  The reference plans over len(ray.nodes()) nodes of 8 GPUs each (milp.py:58-62); here the
     node count is the `nodes` keyword, else SATURN_B200_NODES, else an initialised Ray's node count,
@@ -214,7 +248,7 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     J = len(task_list)
     if J == 0:
         return [[[] for _ in range(NSLOT)]], [], [], [], [], 0.0
-    eng = engine if engine is not None else _engine()
+    eng = engine if engine is not None else _engine(devices)
     T, usable, optindex = build_table(task_list)
     # sentinel cells (executor None) must never be proposed: they are removed from the device table
     # unless the task has nothing else; every remaining finite cell is usable (sentinel = +inf)
@@ -222,6 +256,7 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     for j in range(J):
         if usable[j].any():
             Tdev[j, 0, ~usable[j]] = np.inf
+    _check_horizon(Tdev)
     if nodes is None:
         nodes = _default_nodes()
     nodes = int(nodes)
@@ -260,7 +295,7 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     global last_stats
     last_stats = {"candidates": res.evaluated, "rounds": res.rounds, "search_wall_s": res.wall_s,
                   "device_makespan": res.makespan, "makespan": prop_makespan, "J": J, "chains": chains,
-                  "nodes": nodes,
+                  "nodes": nodes, "devices": len(getattr(eng, "engines", [eng])),
                   "total_wall_s": None, "adopted": True}
 
     # ---- introspection hysteresis (opt-in): the documented intent of milp.py:363-442
@@ -282,6 +317,140 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
                 last_stats["adopted"] = False
     last_stats["total_wall_s"] = time.perf_counter() - t_wall
     return out
+
+
+# ------------------------------------------------------------------------------------------ dense T
+NOT_PROFILED = 1.0e6   # PerformanceEvaluator.py:99  (gpu count outside the task's gpu_range)
+FAILED = 1.0e8         # PerformanceEvaluator.py:106 (every executor failed at this gpu count)
+
+
+def table_from_trials(n_tasks: int, n_executors: int, gpu_ranges, flat_results, max_gpus: int = NSLOT):
+    """The trial runner's raw results as the dense tensor the GPU path ingests.
+
+    `flat_results` is the list PerformanceEvaluator.search collects (PerformanceEvaluator.py:78-93): one
+    `(params, runtime)` per (task, g in the task's gpu_range, executor) in that nesting order, runtime
+    already scaled to the whole job (`:24-26`), `params is None` for a failed trial.  `gpu_ranges[t]` is
+    the task's gpu_range (None = 1..max_gpus).  Returns
+        T[J][S][G] fp32  runtime of task j under executor s on g+1 GPUs; the reference's sentinels where
+                         there is no measurement: 1e6 not profiled (`:99`), 1e8 failed (`:106`)
+        mask[J][S][G]    True where a trial succeeded
+        params[J][S][G]  the executor's tuned parameters (object array, None elsewhere)
+    Instead of collapsing the executor axis into task.strategies on the host (`:101-115`) the solver is
+    given all of it: `solve_table(T, mask)`; `strategies_from_table` gives the dict view."""
+    G = int(max_gpus)
+    T = np.full((n_tasks, n_executors, G), NOT_PROFILED, dtype=np.float32)
+    mask = np.zeros((n_tasks, n_executors, G), dtype=bool)
+    params = np.empty((n_tasks, n_executors, G), dtype=object)
+    it = iter(flat_results)
+    for t in range(n_tasks):
+        rng_t = gpu_ranges[t] if gpu_ranges is not None and gpu_ranges[t] is not None else range(1, G + 1)
+        for g in rng_t:
+            for e in range(n_executors):
+                prm, runtime = next(it)
+                if not 1 <= int(g) <= G:
+                    continue
+                if prm is not None and runtime is not None:
+                    v = np.float32(runtime)
+                    if float(v) < float(runtime):                     # round up, as build_table does
+                        v = np.nextafter(v, np.float32(np.inf))
+                    T[t, e, int(g) - 1] = v
+                    mask[t, e, int(g) - 1] = True
+                    params[t, e, int(g) - 1] = prm
+                else:
+                    T[t, e, int(g) - 1] = FAILED
+    return T, mask, params
+
+
+def strategies_from_table(T, mask, executors=None, params=None, gcount=None):
+    """The compatibility view: what PerformanceEvaluator.py:96-115 would have attached to each task —
+    per task an ordered dict {g: Strategy(executor, g, params, runtime)} over ALL gpu counts, the fastest
+    executor per g (first minimum wins, strict `<` at `:110`), Strategy(None, g, None, 1e6) where nothing was
+    profiled and Strategy(None, g, None, 1e8) where every executor failed."""
+    from .representations import Strategy
+    T = np.asarray(T)
+    mask = np.asarray(mask, dtype=bool)
+    J, S, G = T.shape
+    gcount = list(range(1, G + 1)) if gcount is None else [int(g) for g in gcount]
+    out = []
+    for j in range(J):
+        d = {}
+        for gi, g in enumerate(gcount):
+            ok = mask[j, :, gi]
+            if ok.any():
+                col = np.where(ok, T[j, :, gi], np.inf)
+                e = int(np.argmin(col))                                   # first minimum
+                ex = executors[e] if executors is not None else e
+                d[g] = Strategy(ex, g, params[j, e, gi] if params is not None else None, float(T[j, e, gi]))
+            else:
+                failed = bool((T[j, :, gi] >= FAILED).any())
+                d[g] = Strategy(None, g, None, FAILED if failed else NOT_PROFILED)
+        out.append(d)
+    return out
+
+
+def solve_table(T, mask=None, gcount=None, presolved=None, interval=1000, timeout=500, *,
+                chains: Optional[int] = None, rounds: Optional[int] = None, seed: int = 0,
+                integer_starts: bool = True, engine=None, nodes: Optional[int] = None, devices=None):
+    """solve() on the dense profiler tensor T[J][S][G] (+ mask of usable cells, + gcount[G] GPU counts).
+
+    The table goes to the device un-reduced (sb_set_table: min over strategies with the first-minimum rule
+    and its arg-min on the device, PerformanceEvaluator.py:101-115); the search runs on the reduced view
+    (a slower strategy at the same GPU count is dominated).  Returns the reference's 6-tuple
+    (sta, tga, bss, bna, boa, makespan) — bss[t] is one-hot over the G gpu-count columns, the option order
+    task.strategies has after profiling — plus strategy[J], the index of the winning strategy (executor) of
+    each task's chosen cell.  For the same seed and population the plan equals solve() on the
+    `strategies_from_table` view."""
+    from .search import run_search
+    T = np.ascontiguousarray(T, dtype=np.float32)
+    if T.ndim != 3:
+        raise SolverError("T must be [J][S][G]")
+    J, S, G = T.shape
+    if J == 0:
+        return [[[] for _ in range(NSLOT)]], [], [], [], [], 0.0, np.zeros(0, dtype=np.int64)
+    gcount = list(range(1, G + 1)) if gcount is None else [int(g) for g in gcount]
+    if len(gcount) != G or len(set(gcount)) != G or not all(1 <= g <= NSLOT for g in gcount):
+        raise SolverError("gcount must hold %d distinct GPU counts in 1..%d" % (G, NSLOT))
+    usable = np.isfinite(T) & (T >= 0) if mask is None else (np.asarray(mask, dtype=bool) & np.isfinite(T))
+    if mask is None:
+        usable &= T < NOT_PROFILED
+    Tdev = np.where(usable, T, np.inf).astype(np.float32)
+    for j in np.nonzero(~usable.reshape(J, -1).any(axis=1))[0]:
+        Tdev[j] = np.where(np.isfinite(T[j]), T[j], np.inf)      # nothing usable: the sentinels are all it has
+    if not np.isfinite(Tdev.reshape(J, -1)).any(axis=1).all():
+        raise SolverError("a task has no finite cell in T")
+    _check_horizon(Tdev)
+    eng = engine if engine is not None else _engine(devices)
+    nodes = int(_default_nodes() if nodes is None else nodes)
+    eng.set_table(Tdev, gcount, sentinel=float("inf"), nodes=nodes)
+    if chains is None:
+        chains = int(os.environ.get("SATURN_B200_CHAINS", 0))
+        if chains <= 0:
+            wave = eng.search_wave(reduced=True)
+            chains = max(1, round((1 << 17) / wave)) * wave if wave > 0 else 1 << 17
+    if rounds is None:
+        rounds = int(os.environ.get("SATURN_B200_ROUNDS", 400))
+    budget = min(float(os.environ.get("SATURN_B200_BUDGET_S", 20.0)), float(timeout))
+    col_of_k = {g: gi for gi, g in enumerate(gcount)}
+    warm = None
+    if presolved is not None:
+        class _Opt:                      # the option list a task has in this view: every gpu-count column
+            strategies = {g: None for g in gcount}
+        warm = candidate_from_arrays([_Opt] * J, presolved, nodes)
+    res = run_search(eng, chains=chains, rounds=rounds, seed=seed, integer_starts=integer_starts, reduced=True,
+                     time_budget_s=budget, patience=max(40, rounds // 4), warm=warm)
+    dec = eng.decode(res.opt, res.prio, integer_starts=integer_starts, reduced=True)
+    gpus = dec["gpus"].astype(np.int64)
+    chosen = np.array([col_of_k[int(k)] for k in gpus], dtype=np.int64)
+    position = np.empty(J, dtype=np.int64)
+    position[res.prio.astype(np.int64)] = np.arange(J)
+    arrays = plan_to_arrays([G] * J, chosen, dec["start"], dec["slotmask"], position, nodes=nodes, node_of=dec["node"])
+    strategy = dec["strategy"].astype(np.int64)
+    makespan = max(float(dec["start"][j]) + float(T[j, strategy[j], chosen[j]]) for j in range(J))
+    global last_stats
+    last_stats = {"candidates": res.evaluated, "rounds": res.rounds, "search_wall_s": res.wall_s,
+                  "device_makespan": res.makespan, "makespan": makespan, "J": J, "chains": chains, "nodes": nodes,
+                  "devices": len(getattr(eng, "engines", [eng])), "total_wall_s": None, "adopted": True}
+    return arrays + (makespan, strategy)
 
 
 # ------------------------------------------------------------------------------------------ decode

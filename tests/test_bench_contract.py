@@ -27,6 +27,11 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms print the same `config` object for the headline run
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.static_config(True)
+    assert d["cpu_baseline"]["cores"] <= (os.cpu_count() or 1) and "physical cores" in d["run"]["cores_how"]
 
 
 @pytest.mark.gpu
@@ -41,3 +46,7 @@ def test_our_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert d["gpu_launches"] == 4 and d["value"] > 1e8
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.static_config(True)
+    assert d["e2e"]["candidates_per_gpu_per_step"] == d["run"]["candidates_per_gpu_per_step"]   # same batch as `value`

@@ -88,3 +88,61 @@ def test_peer_memory_exchange_and_sharded_search():
     (r0, ok0, mk0, ev0, o0, n0), (r1, ok1, mk1, ev1, o1, n1) = out
     assert ok0 and ok1
     assert mk0 == mk1 == ev0 == ev1 and o0 == o1 and n0 == n1
+
+
+def test_one_process_multi_device_search():
+    """sb_search_run_multi: two devices driven by ONE process (saturn.solver.solve(..., devices=2)).  The RNG is
+    counter-based on global chain ids, so device i of the sharded run walks exactly the chains a single-device
+    run with chain_base = i * chains walks: the sharded result must be the better of the two single runs, and
+    the plan must come back through the reference API."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import ref_eval as R
+    from saturn_b200.engine import Engine, MultiEngine
+    from saturn_b200.search import run_search
+    J, S, G = 96, 4, 8
+    T, valid = R.synth_table(J, S, G, seed=2)
+    chains, rounds = 8192, 48
+    singles = []
+    for d in range(2):
+        e = Engine(d)
+        e.set_table(T)
+        r = e.search_run(chains, rounds, seed=5, chain_base=d * chains, reduced=True, sync_every=16)
+        singles.append(r)
+        e.close()
+    me = MultiEngine([0, 1])
+    me.set_table(T)
+    r = me.search_run(chains, rounds, seed=5, reduced=True, sync_every=16, record_history=True)
+    best = min(singles, key=lambda x: x["key"])
+    assert r["key"] == best["key"] and r["makespan"] == best["makespan"]
+    assert np.array_equal(r["opt"], best["opt"]) and np.array_equal(r["prio"], best["prio"])
+    assert r["evaluated"] == singles[0]["evaluated"] + singles[1]["evaluated"]
+    assert r["history"][-1][2] == r["makespan"]
+    # through the host API: run_search routes a MultiEngine to sb_search_run_multi
+    res = run_search(me, chains=chains, rounds=rounds, seed=5, reduced=True, use_dist=False, heuristic_seeds=True)
+    assert res.makespan == r["makespan"] and np.array_equal(res.opt, r["opt"])
+    tab = R.canon_table(T, range(1, 9))
+    tmin, _ = R.reduce_table(tab)
+    mk = float(R.list_schedule(tmin[:, None, :], r["opt"], r["prio"], True, np.float32)[0])
+    assert mk == r["makespan"]
+    me.close()
+    # and saturn.solver.solve(..., devices=2) returns a plan the reference's constraint set accepts
+    from saturn_b200 import Strategy, solve
+    from saturn_b200 import solver as Sv
+
+    class _T:
+        def __init__(self, name, strategies):
+            self.name, self.strategies, self.selected_strategy = name, strategies, None
+
+        def select_strategy(self, s):
+            self.selected_strategy = s
+
+    rng = np.random.default_rng(0)
+    tasks = [_T("t%d" % t, {g: Strategy("x", g, {}, float(rng.uniform(500, 4000)) / g ** 0.8) for g in (1, 2, 4, 8)})
+             for t in range(12)]
+    out = solve(tasks, None, chains=4096, rounds=30, devices=2)
+    assert Sv.last_stats["devices"] == 2 and Sv.last_stats["candidates"] >= 2 * 4096 * 31
+    tuples = [[(g, s.runtime) for g, s in t.strategies.items()] for t in tasks]
+    assert R.milp_constraints_hold(tuples, *out[:5], out[5]) == []
+    one = solve(tasks, None, chains=4096, rounds=30, devices=1)
+    assert out[5] <= one[5] * (1 + 1e-9)

@@ -311,3 +311,58 @@ def test_plain_c_host_plans_through_the_abi(tmp_path, J):
     lpt_order = np.argsort(-tmin[:, 7], kind="stable")
     lpt = R.list_schedule(tmin[:, None, :], np.full(J, 7, np.uint8), lpt_order, True, np.float32)[0]
     assert mk <= lpt
+
+
+# ------------------------------------------------------------------------------------------ round 2
+def test_solve_table_equals_solve_on_the_reduced_view(engine):
+    """the dense T[J][S][G] + mask entry gives the plan solve() gives on the task.strategies view
+    the profiler would have built from the same trials (same seed, same population), plus the winning
+    strategy per task."""
+    from conftest import DuckTask
+    from saturn_b200 import convert_into_comprehensible, solve, solve_table, strategies_from_table
+    from saturn_b200 import solver as S
+    J, Sx, G = 24, 4, 8
+    T, valid = R.synth_table(J, Sx, G, seed=12)
+    strategies = strategies_from_table(T, valid, executors=["e%d" % s for s in range(Sx)])
+    tasks = [DuckTask("t%d" % j, strategies[j]) for j in range(J)]
+    a = solve(tasks, None, chains=8192, rounds=40, seed=3, engine=engine)
+    dev_a = S.last_stats["device_makespan"]
+    b = solve_table(T, valid, chains=8192, rounds=40, seed=3, engine=engine)
+    assert S.last_stats["device_makespan"] == dev_a
+    assert b[5] == pytest.approx(a[5], rel=1e-12)
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and a[4] == b[4]
+    strategy = b[6]
+    npt, tdd, starts = convert_into_comprehensible(tasks, b[2], b[4], b[1], b[3], b[0])
+    for j, t in enumerate(tasks):
+        g = t.selected_strategy.gpu_apportionment
+        assert valid[j, strategy[j], g - 1]
+        assert T[j, strategy[j], g - 1] == np.float32(t.selected_strategy.runtime)
+        assert t.selected_strategy.executor == "e%d" % strategy[j]
+    # a previous plan warm-starts the dense entry too, and a table without a mask treats sentinels as unusable
+    c = solve_table(T, None, presolved=b[:6], chains=4096, rounds=10, seed=4, engine=engine)
+    assert c[5] <= b[5] * (1 + 1e-6)
+    for j in range(J):
+        g = int(np.argmax(c[2][j])) + 1
+        assert T[j, c[6][j], g - 1] < 1e6
+
+
+@pytest.mark.parametrize("J,nodes", [(64, 1), (256, 1), (300, 1), (700, 1), (1024, 1), (64, 3), (700, 2)])
+def test_initial_population_rows_are_valid(engine, J, nodes):
+    """The shared-memory initialisation kernel (and the position-major one for large J) emits, for every
+    chain, a permutation and existing table cells; two populations from one seed are identical and the
+    incumbent of the freshly scored population decodes to its own makespan."""
+    T, valid = R.synth_table(J, 3, 8, seed=J)
+    engine.set_table(T, nodes=nodes)
+    chains = 5000
+    engine.search_init(chains, seed=9, chain_base=17, reduced=True)
+    assert engine.search_validate() == 0
+    o1, p1, mk1, key1 = engine.search_best()
+    assert sorted(p1.tolist()) == list(range(J))
+    engine.search_init(chains, seed=9, chain_base=17, reduced=True)
+    o2, p2, mk2, key2 = engine.search_best()
+    assert key1 == key2 and np.array_equal(o1, o2) and np.array_equal(p1, p2)
+    dec = engine.decode(o1, p1, reduced=True)
+    assert dec["makespan"] == mk1
+    engine.search_init(chains, seed=10, chain_base=17, reduced=True)
+    assert engine.search_best()[3] != key1
+    engine.set_table(T)

@@ -256,3 +256,114 @@ def test_forecast_matches_reference_forecast():
         for task, after in zip(tasks, case["after"]):
             assert task.total_batches == after["total_batches"]
             assert [[g, s.runtime] for g, s in task.strategies.items()] == after["runtimes"]
+
+
+# ------------------------------------------------------------------------------------------ round 2
+def test_alias_package_falls_through_to_an_installed_reference():
+    """`import saturn` is this repository's alias; submodules it does not implement resolve in a reference
+    distribution when one is on sys.path (saturn_b200/_alias.py) and raise a clear ImportError otherwise."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import saturn, saturn.solver, saturn.core.representations as Rp, saturn.executor as E
+assert saturn.solver.solve.__module__ == "saturn_b200.solver"
+assert Rp.Task.__module__ == "saturn_b200.representations"
+try:
+    import saturn.library
+    raise SystemExit("saturn.library must not resolve without a reference distribution")
+except ImportError:
+    pass
+try:
+    E.execute
+    raise SystemExit("saturn.executor.execute must not resolve without a reference distribution")
+except ImportError as e:
+    assert "not part of the B200 solver drop-in" in str(e)
+ref = "/root/reference"
+import os
+if os.path.isdir(ref):
+    sys.path.append(ref)
+    for m in [m for m in sys.modules if m == "saturn" or m.startswith("saturn.")]:
+        del sys.modules[m]
+    import saturn, saturn.solver, saturn.library
+    assert saturn.library.__file__.startswith(ref)                      # fell through
+    assert saturn.solver.solve.__module__ == "saturn_b200.solver"       # the drop-in still wins
+    assert saturn.orchestrate.__module__ == "saturn_b200.orchestrator"
+print("ok")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def _profiler_reduction(n_tasks, executors, gpu_ranges, flat, max_gpus):
+    """PerformanceEvaluator.py:96-115 restated literally on (executor name, params, runtime) tuples."""
+    out = []
+    idx = 0
+    for t in range(n_tasks):
+        d = {g: (None, None, 1000000) for g in range(1, max_gpus + 1)}               # :96-99
+        rng_t = gpu_ranges[t] if gpu_ranges[t] is not None else list(range(1, max_gpus + 1))
+        for g in rng_t:
+            chosen = (None, None, 1e8)                                                   # :106
+            for e in executors:
+                params, runtime = flat[idx]
+                idx += 1
+                if params is not None and runtime < chosen[2]:                            # :109-110
+                    chosen = (e, params, runtime)
+            d[g] = chosen
+        out.append(d)
+    return out
+
+
+def test_dense_table_from_trials_matches_the_profiler_reduction():
+    """table_from_trials + strategies_from_table == the dict the trial runner attaches to every task
+    (PerformanceEvaluator.py:96-115): fastest executor per GPU count, first minimum on ties, 1e6 where the
+    count is outside the task's gpu_range, 1e8 / executor None where every executor failed."""
+    from saturn_b200.solver import FAILED, NOT_PROFILED, strategies_from_table, table_from_trials
+    rng = np.random.default_rng(4)
+    executors = ["spill", "ddp", "fsdp"]
+    n_tasks, G = 7, 8
+    gpu_ranges = [None, [1, 2, 4], [2, 4, 8], None, [8], [1], [3, 5, 6]]
+    flat = []
+    for t in range(n_tasks):
+        for g in (gpu_ranges[t] or range(1, G + 1)):
+            for e in range(len(executors)):
+                if rng.uniform() < 0.3:
+                    flat.append((None, None))
+                else:
+                    flat.append(({"bs": int(rng.integers(1, 9))}, float(np.float32(rng.uniform(100, 5000)))))
+    flat[0] = ({"bs": 1}, 777.0)
+    flat[1] = ({"bs": 2}, 777.0)                  # a tie: the first executor must win
+    flat[2] = (None, None)
+    T, mask, params = table_from_trials(n_tasks, len(executors), gpu_ranges, flat, max_gpus=G)
+    assert T.shape == mask.shape == (n_tasks, len(executors), G) and T.dtype == np.float32
+    got = strategies_from_table(T, mask, executors, params)
+    want = _profiler_reduction(n_tasks, executors, gpu_ranges, flat, G)
+    for t in range(n_tasks):
+        assert list(got[t].keys()) == list(range(1, G + 1))
+        for g in range(1, G + 1):
+            e, prm, rt = want[t][g]
+            s = got[t][g]
+            assert s.executor == e and s.gpu_apportionment == g
+            assert s.runtime == pytest.approx(rt, rel=1e-6) and (s.parameters == prm)
+    assert got[0][1].executor == "spill" and got[0][1].runtime == 777.0
+    assert (T[~mask] >= NOT_PROFILED).all() and set(np.unique(T[~mask])) <= {np.float32(NOT_PROFILED), np.float32(FAILED)}
+    # the oracle's device-side statement of the same reduction (first minimum over strategies)
+    tab = R.canon_table(np.where(mask, T, np.inf), range(1, G + 1))
+    tmin, args = R.reduce_table(tab)
+    for t in range(n_tasks):
+        for g in range(1, G + 1):
+            if mask[t, :, g - 1].any():
+                assert tmin[t, g - 1] == np.float32(got[t][g].runtime)
+                assert executors[int(args[t, g - 1])] == got[t][g].executor
+
+
+def test_fp32_horizon_guard():
+    """Schedule times are exact integers in fp32 only below 2^24 s: a table that can cross it is refused."""
+    from saturn_b200.solver import SolverError, _check_horizon
+    T = np.full((20, 1, 8), np.inf, dtype=np.float32)
+    T[:, 0, 0] = 1.0e6
+    with pytest.raises(SolverError):
+        _check_horizon(T)
+    T[:, 0, 0] = 36000.0
+    _check_horizon(T)
