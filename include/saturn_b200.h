@@ -286,6 +286,13 @@ int sb_search_is_fused(sb_handle* h);
 /* sb_validate on the search population as it stands (every chain's rows: a permutation and existing table
  * cells), whatever encoding the population is kept in.  Synchronous; bad_rows (host) = offending chains. */
 int sb_search_validate(sb_handle* h, int64_t* bad_rows);
+/* Test hook.  Fused rounds of the tile kernel score a proposal incrementally: the chains of a warp make their
+ * moves inside one window of 32 schedule positions per round and resume the list schedule from the state
+ * snapshotted in front of that window.  With bit 0x08000000 set in sb_search_params.flags every such score is
+ * also recomputed from position 0; this returns how many differed (must be 0).  Bits 0x10000000 (same
+ * windowed moves, always scored from position 0) and 0x04000000 (round-1 move generator) select the
+ * reference behaviours the tests and profiles compare against. */
+int sb_search_verify_count(sb_handle* h, uint64_t* mismatches);
 /* candidates evaluated so far by this handle's searches */
 int sb_search_stats(sb_handle* h, int64_t* evaluated, int64_t* rounds_done);
 

@@ -20,7 +20,7 @@ SYMBOLS = [
     "sb_set_sentinel", "sb_get_reduced", "sb_eval", "sb_last_eval_path", "sb_validate", "sb_eval_host", "sb_eval_full",
     "sb_decode", "sb_xchg_create", "sb_xchg_connect", "sb_xchg_connect_local", "sb_xchg_post", "sb_xchg_reduce", "sb_xchg_check",
     "sb_search_init", "sb_search_round", "sb_search_best_key_ptr", "sb_search_best",
-    "sb_search_inject", "sb_search_resample", "sb_search_seed_lpt", "sb_search_run", "sb_search_run_multi", "sb_search_wave", "sb_search_is_fused", "sb_search_stats", "sb_search_validate",
+    "sb_search_inject", "sb_search_resample", "sb_search_seed_lpt", "sb_search_run", "sb_search_run_multi", "sb_search_wave", "sb_search_is_fused", "sb_search_stats", "sb_search_validate", "sb_search_verify_count",
 ]
 
 
@@ -97,6 +97,7 @@ def load():
         "sb_search_is_fused": [vp],
         "sb_search_stats": [vp, C.POINTER(i64), C.POINTER(i64)],
         "sb_search_validate": [vp, C.POINTER(i64)],
+        "sb_search_verify_count": [vp, C.POINTER(C.c_uint64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

@@ -36,9 +36,15 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
+    tmp = SO + ".%d.tmp" % os.getpid()      # never leave a half-written library where a snapshot could pick it up
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, SO)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return SO
 
 

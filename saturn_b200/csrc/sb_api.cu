@@ -50,6 +50,11 @@ struct SearchState {
   // the allocation is kept across sb_search_init / sb_set_table calls while its shape stays the same (a
   // re-planning loop solves the same task set every interval: no cudaMalloc / cudaFree per solve)
   long long alloc_chains = 0, alloc_stride_o = 0, alloc_stride_p = 0;
+  // incremental rounds (tile kernel, one node): boundary snapshots, see SearchFuse::snap
+  float* snap = nullptr;
+  size_t snap_bytes = 0;
+  unsigned long long* verify_bad = nullptr;
+  bool win = false, inc = false, verify = false;
   SearchDev alloc;  // the pointers as allocated (s.d's cur / prop pairs trade places when resampling)
 };
 
@@ -112,6 +117,9 @@ static void free_search(sb_handle* h) {
   s.alloc_chains = s.alloc_stride_o = s.alloc_stride_p = 0;
   s.cand_o = s.cand_p = nullptr;
   s.tail_counter = nullptr;
+  s.snap = nullptr;
+  s.snap_bytes = 0;
+  s.verify_bad = nullptr;
 }
 
 static void free_staging(sb_handle* h) {
@@ -744,8 +752,39 @@ int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_
   s.rounds_done = 0;
   s.launches = 0;
   s.fused_ok = d.pos || (!no_fused && mode != 0);
-  // automatic cadence: resampling is nearly free inside the tile kernel, a full copy of the population elsewhere
-  if (s.p.resample_every < 0) s.p.resample_every = (s.fused_ok && !d.pos) ? 2 : 4;
+  // incremental rounds: fused kernels, one node, at least two windows (tile kernel: windows of kSnapPos
+  // positions; position-major kernel: windows of whole 32-position blocks, at most 32 windows).  Test hooks in
+  // the flags: 0x04000000 = round-1 move generator (no windows), 0x10000000 = windowed moves scored from
+  // position 0, 0x08000000 = verify
+  int nwin = (J + kSnapPos - 1) / kSnapPos;
+  if (d.pos) {
+    const int nout = (J + 31) / 32, wblk = (nout + 31) / 32;
+    nwin = (nout + wblk - 1) / wblk;
+  }
+  s.win = s.fused_ok && h->nodes == 1 && nwin >= 2 && nwin <= 32 && !(p->flags & 0x04000000u);
+  s.inc = s.win && !(p->flags & 0x10000000u);
+  s.verify = s.inc && (p->flags & 0x08000000u);
+  // automatic cadence: resampling is nearly free inside the tile kernel; elsewhere it is a full copy of the
+  // population and ends a launch (an incremental launch starts with one unmodified pass, so longer is better)
+  if (s.p.resample_every < 0) s.p.resample_every = (s.fused_ok && !d.pos) ? 2 : (s.inc ? 8 : 4);
+  if (s.inc) {
+    const size_t need = static_cast<size_t>((d.chains + 31) / 32) * (nwin - 1) * 2 * 9 * 32 * sizeof(float);
+    if (s.snap_bytes < need) {
+      if (s.snap) {  // grow: drop the old block from the table
+        for (int i = 0; i < s.nblocks; ++i)
+          if (s.blocks[i] == s.snap) { cudaFree(s.snap); s.blocks[i] = s.blocks[--s.nblocks]; break; }
+        s.snap = nullptr;
+        s.snap_bytes = 0;
+      }
+      if ((rc = search_alloc(s, reinterpret_cast<void**>(&s.snap), need))) { s.ready = false; return rc; }
+      s.snap_bytes = need;
+    }
+    if (!s.verify_bad && (rc = search_alloc(s, reinterpret_cast<void**>(&s.verify_bad), sizeof(unsigned long long)))) {
+      s.ready = false;
+      return rc;
+    }
+    CK(cudaMemsetAsync(s.verify_bad, 0, sizeof(unsigned long long), h->stream));
+  }
   return SB_OK;
 }
 
@@ -769,6 +808,9 @@ static SearchFuse make_fuse(const SearchState& s, int round, int n) {
   for (int r = 0; r < n; ++r) sf.temperature[r] = round_temperature(s, round + r);
   sf.resample_every = s.p.resample_every > 0 ? s.p.resample_every : 0;
   sf.deal = static_cast<int>(s.launches & 1);
+  sf.win = s.win ? 1 : 0;
+  sf.snap = s.inc ? s.snap : nullptr;
+  sf.verify_bad = s.verify ? s.verify_bad : nullptr;
   sf.keep.counter = s.tail_counter;
   sf.keep.keys = s.d.keys;
   sf.keep.best_o = s.d.best_o; sf.keep.best_p = s.d.best_p;
@@ -1175,6 +1217,21 @@ int sb_search_validate(sb_handle* h, int64_t* bad_rows) {
   CK(cudaMemcpyAsync(&bad, h->d_scratch, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   *bad_rows = static_cast<int64_t>(bad);
+  return SB_OK;
+}
+
+int sb_search_verify_count(sb_handle* h, uint64_t* mismatches) {
+  int rc = use_device(h);
+  if (rc) return rc;
+  if (!mismatches) return fail(SB_ERR_ARG, "mismatches is null");
+  SearchState& s = h->search;
+  if (!s.ready) return fail(SB_ERR_STATE, "sb_search_init has not been called");
+  *mismatches = 0;
+  if (!s.verify_bad) return SB_OK;
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, s.verify_bad, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *mismatches = v;
   return SB_OK;
 }
 

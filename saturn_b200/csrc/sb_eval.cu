@@ -214,6 +214,55 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       }
       return st.result();
     };
+    // SEARCH rounds: score the lane's rows from window `w0` on (warp-uniform).  w0 > 0 resumes from the
+    // snapshot taken in front of that window (buffer bit w0-1 of `par`); `save` stores the state in front of
+    // every later window into the OTHER buffer (the proposal's boundary states; the caller flips the bits of
+    // `par` if it accepts the move).  Snapshot = the 8 sorted slot times + the running makespan; a completion
+    // parked in `pend` is always folded at a window boundary (even number of steps per window).
+    [[maybe_unused]] auto eval_from = [&](const uint8_t* prio_row_s, int w0, uint32_t par, bool save,
+                                          float* snap_t) -> float {
+      const int J = a.J;
+      constexpr int STEPS = 16 / PB;            // schedule positions per 128-bit shared-memory read
+      constexpr int CPW = kSnapPos / STEPS;     // reads per window
+      const int nwin = (J + kSnapPos - 1) / kSnapPos;
+      if (w0 == 0) {
+        st.reset(a.nodes);
+      } else {
+        const float* sp = snap_t + (((w0 - 1) * 2 + ((par >> (w0 - 1)) & 1u)) * 9) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st.f[i] = __ldcg(sp + i * 32);
+        st.mk = __ldcg(sp + 8 * 32);
+        st.pend = 0.f;
+      }
+      const uint4* prow = reinterpret_cast<const uint4*>(prio_row_s);
+#pragma unroll 1
+      for (int w = w0; w < nwin; ++w) {
+        if (save && w > w0) {
+          float* sp = snap_t + (((w - 1) * 2 + (((par >> (w - 1)) & 1u) ^ 1u)) * 9) * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) __stcg(sp + i * 32, st.f[i]);
+          __stcg(sp + 8 * 32, fmaxf(st.mk, st.pend));
+        }
+#pragma unroll
+        for (int cc = 0; cc < CPW; ++cc) {
+          const int c = w * CPW + cc;
+          if (c * STEPS < J) {
+            const uint4 p = prow[c];
+            const uint32_t wd[4] = {p.x, p.y, p.z, p.w};
+            if ((c + 1) * STEPS <= J) {
+#pragma unroll
+              for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(wd, t), t & 1);
+            } else {
+              const int rem = J - c * STEPS;
+#pragma unroll
+              for (int t = 0; t < STEPS; ++t)
+                if (t < rem) st.step(prio_at<PB>(wd, t), t & 1);
+            }
+          }
+        }
+      }
+      return st.result();
+    };
     if (!SEARCH) {
       float mk = 0.f;
       if (active) {
@@ -236,6 +285,15 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       const uint64_t gid = a.sf.chain_base + static_cast<uint64_t>(c);
       float cm = active ? a.sf.cur_mk[c] : 0.f;
       bool moving = active;  // false from the round in which this lane lowers the global best key
+      // incremental rounds (one node): boundary snapshots of this tile, filled by one unmodified pass
+      const bool inc = !MULTI && a.sf.snap != nullptr;
+      const bool win = !MULTI && a.sf.win != 0;
+      const int nwin = (a.J + kSnapPos - 1) / kSnapPos;
+      float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
+      uint32_t par = 0;  // bit w-1: which buffer holds the current candidate's state in front of window w
+      if (inc) {
+        (void)eval_from(prow_s, 0, ~0u, true, snap_t);  // writes buffer 0 of every boundary
+      }
 #pragma unroll 1
       for (int r = 0; r < a.sf.nrounds; ++r) {
         const int round = a.sf.round + r;
@@ -264,16 +322,57 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
             if (take) { reinterpret_cast<uint4*>(prow_s)[i] = v; gp[i] = v; }
             __syncwarp();
           }
+          if (inc) {
+            // ... and its boundary snapshots: word by word from the rival's current buffers into this lane's
+            // current buffers (same read-all-then-write discipline)
+            const uint32_t rpar = __shfl_sync(0xffffffffu, par, rival);
+            for (int b = 0; b < nwin - 1; ++b) {
+              const float* src = snap_t + ((b * 2 + ((rpar >> b) & 1u)) * 9) * 32 + rival;
+              float* dst = snap_t + ((b * 2 + ((par >> b) & 1u)) * 9) * 32 + lane;
+              float v[9];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) v[i] = __ldcg(src + i * 32);
+              __syncwarp();
+              if (take) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) __stcg(dst + i * 32, v[i]);
+              }
+              __syncwarp();
+            }
+          }
           if (take) {
             cm = rcm;
             a.sf.cur_mk[c] = rcm;
           }
         }
+        // the window of this round: one draw per (warp's first chain, round), the same in all 32 lanes
+        int w0 = 0;
+        if (win) {
+          const uint64_t wr = rng_u64(a.sf.seed ^ 0x31d0ull, a.sf.chain_base + static_cast<uint64_t>(a.sf.deal ? tile : b0),
+                                      static_cast<uint64_t>(round));
+          w0 = static_cast<int>(bounded32(wr, nwin));
+        }
         Move mv;
         mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = 0;
-        if (moving) mv = apply_move<PB>(a.sf, round, a.J, gid, orow_s, prow_s);
+        if (moving) {
+          if (win) {
+            const int p0 = w0 * kSnapPos;
+            mv = apply_move_win<PB>(a.sf, round, a.J, gid, orow_s, prow_s, p0, min(kSnapPos, a.J - p0));
+          } else {
+            mv = apply_move<PB>(a.sf, round, a.J, gid, orow_s, prow_s);
+          }
+        }
         __syncwarp();  // shadowing lanes read lane 0's rows
-        float mk = evaluate(prow_s);
+        float mk;
+        if (inc) {
+          mk = eval_from(prow_s, w0, par, true, snap_t);
+          if (a.sf.verify_bad != nullptr) {
+            const float full = eval_from(prow_s, 0, par, false, snap_t);
+            if (active && __float_as_uint(full) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
+          }
+        } else {
+          mk = evaluate(prow_s);
+        }
         if (moving) {
           bool acc = mk <= cm;
           const float temp = a.sf.temperature[r];
@@ -287,6 +386,8 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
               write_back<PB>(mv, orow_s, prow_s, a.sf.cur_o + c * a.stride_o, a.sf.cur_p + c * a.stride_p);
               a.sf.cur_mk[c] = mk;
               cm = mk;
+              // the boundary states this proposal wrote (windows after w0) are now the current ones
+              if (inc) par ^= (w0 + 1 < nwin) ? (~0u << w0) : 0u;
             }
           } else {
             undo_move<PB>(mv, orow_s, prow_s);

@@ -55,6 +55,7 @@ struct EvalCall {
 
 // what the fused search round needs besides an EvalCall (see k_eval_tiles<..., SEARCH = true>)
 constexpr int kMaxFusedRounds = 8;
+constexpr int kSnapPos = 32;  // schedule positions per window / between state snapshots (incremental search rounds)
 struct SearchFuse {
   float* cur_mk = nullptr;        // [chains] makespan of each chain's current candidate
   uint8_t* cur_o = nullptr;       // writable views of the rows the EvalCall reads
@@ -71,6 +72,17 @@ struct SearchFuse {
   // `deal` changes which chains share a warp: 0 = chain = tile * 32 + lane, 1 = chain = lane * ntiles + tile.
   int resample_every = 0;
   int deal = 0;
+  // Incremental re-evaluation (snap != nullptr; one node only).  Every round a WARP draws one window of
+  // kSnapPos schedule positions and its 32 chains make their moves inside that window (windowed moves:
+  // `win` = 1), so that all of them can resume the list schedule from the same place: the sorted slot
+  // state + running makespan of a chain's CURRENT candidate is snapshotted at every window boundary
+  // ([tile][boundary][2 buffers][9 words][32 lanes] floats in HBM/L2, coalesced, valid for one launch), a
+  // proposal is scored from the snapshot in front of its window and writes its own boundary states into
+  // the other buffer; accepting the move flips which buffer is current (a per-lane bit per boundary), so a
+  // rejected move costs nothing to undo.  An unmodified pass at the start of the launch fills the buffers.
+  int win = 0;                    // 1: moves are drawn inside a per-warp window (also without snapshots)
+  float* snap = nullptr;          // scratch, (ntiles * nbound * 2 * 9 * 32) floats; nullptr = score every proposal from position 0
+  unsigned long long* verify_bad = nullptr;  // test hook: also score from position 0 and count differing results here
   // keep-best in the kernel's tail (KeepBest::counter != nullptr): the CTA that finishes last copies the
   // incumbent's rows when the population's best key improved — saves the separate one-warp launch per round
   struct KeepBest {

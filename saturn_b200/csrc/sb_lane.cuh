@@ -233,6 +233,65 @@ __device__ __forceinline__ Move apply_move(const SearchFuse& sf, int round, int 
   return m;
 }
 
+// Windowed form of apply_move (incremental rounds, see SearchFuse::snap): the first schedule position a move
+// changes lies inside [w0, w0 + wlen), positions before w0 are untouched.  Same move kinds and mix; a job is
+// addressed through its position (the option of the job scheduled i-th changes), a swap pairs a position of the
+// window with any later-or-equal position, a re-insertion moves a job forward from the window or back into it.
+template <int PB>
+__device__ __forceinline__ Move apply_move_win(const SearchFuse& sf, int round, int J, uint64_t gid, uint8_t* orow,
+                                               uint8_t* prow, int w0, int wlen) {
+  Move m;
+  m.kind = 0; m.a = 0; m.b = 0; m.va = 0; m.vb = 0;
+  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * round + 0);
+  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * round + 1);
+  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * round + 2);
+  const uint32_t kind = bounded32(r0, 100);
+  const int a = w0 + static_cast<int>(bounded32(r1, wlen));
+  if (kind < 30) {  // change the option of the job scheduled a-th
+    const int j = smem_prio_ld<PB>(prow, a);
+    const int n = sf.nvalid[j];
+    if (n > 1) {
+      const int pick = bounded32(r2, n - 1);
+      const uint8_t curv = orow[j];
+      uint8_t nv = sf.vopt[j * kSlots + pick];
+      if (nv == curv) nv = sf.vopt[j * kSlots + n - 1];
+      orow[j] = nv;
+      m.kind = 1; m.a = j; m.va = curv;
+      return m;
+    }
+  }
+  const int tail = J - w0;  // positions from the window's start on
+  if (tail < 2) return m;
+  if (kind < 70) {  // swap position a with another position >= w0
+    int b = w0 + static_cast<int>(bounded32(r2, tail - 1));
+    if (b >= a) ++b;
+    const int va = smem_prio_ld<PB>(prow, a), vb = smem_prio_ld<PB>(prow, b);
+    smem_prio_st<PB>(prow, a, vb);
+    smem_prio_st<PB>(prow, b, va);
+    m.kind = 2; m.a = a; m.b = b; m.va = va; m.vb = vb;
+    return m;
+  }
+  // re-insertion over up to 48 places: the job at a moves later, or a job from later moves to a
+  const int span = J - 1 < 48 ? J - 1 : 48;
+  const uint32_t dd = bounded32(r2, 2 * span);
+  int b = a + 1 + static_cast<int>(dd >> 1);
+  if (b > J - 1) b = J - 1;
+  if (b == a) return m;
+  if (dd & 1) {  // a -> b
+    const int va = smem_prio_ld<PB>(prow, a);
+    for (int i = a; i < b; ++i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i + 1));
+    smem_prio_st<PB>(prow, b, va);
+    m.va = a; m.vb = b;
+  } else {  // b -> a
+    const int vb = smem_prio_ld<PB>(prow, b);
+    for (int i = b; i > a; --i) smem_prio_st<PB>(prow, i, smem_prio_ld<PB>(prow, i - 1));
+    smem_prio_st<PB>(prow, a, vb);
+    m.va = b; m.vb = a;
+  }
+  m.kind = 3; m.a = a; m.b = b;
+  return m;
+}
+
 // A rejected move is taken back so that the rows in shared memory stay the chain's current candidate
 // (several rounds run on the same tile, see k_eval_tiles).
 template <int PB>

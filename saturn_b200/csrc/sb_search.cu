@@ -365,6 +365,38 @@ __device__ __forceinline__ PosMove make_pos_move(const SearchFuse& sf, int round
   return m;
 }
 
+// Windowed form (incremental rounds): the first position the move changes lies in [p0, p0 + plen).
+template <int PB>
+__device__ __forceinline__ PosMove make_pos_move_win(const SearchFuse& sf, int round, int J, uint64_t gid,
+                                                     const uint8_t* og, const uint8_t* pg, int p0, int plen) {
+  PosMove m;
+  m.kind = 0; m.a = m.b = m.va = m.vb = m.oa = m.ob = 0;
+  const uint64_t r0 = rng_u64(sf.seed, gid, 4ull * round + 0);
+  const uint64_t r1 = rng_u64(sf.seed, gid, 4ull * round + 1);
+  const uint64_t r2 = rng_u64(sf.seed, gid, 4ull * round + 2);
+  const uint32_t kind = bounded(r0, 100);
+  const int a = p0 + static_cast<int>(bounded(r1, plen));
+  if (kind < 30) {  // change the option of the job at position a
+    const int j = prio_ld<PB>(pg, a);
+    const int n = sf.nvalid[j];
+    if (n > 1) {
+      const int cur = og[a];
+      int nv = sf.vopt[j * kSlots + bounded(r2, n - 1)];
+      if (nv == cur) nv = sf.vopt[j * kSlots + n - 1];
+      m.kind = 1; m.a = a; m.oa = nv;
+      return m;
+    }
+  }
+  const int tail = J - p0;
+  if (tail < 2) return m;
+  int b = p0 + static_cast<int>(bounded(r2, tail - 1));
+  if (b >= a) ++b;
+  m.kind = 2; m.a = a; m.b = b;
+  m.va = prio_ld<PB>(pg, a); m.vb = prio_ld<PB>(pg, b);
+  m.oa = og[a]; m.ob = og[b];
+  return m;
+}
+
 template <int PB, bool INT, bool MULTI>
 __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -405,15 +437,34 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     const long long cr = active ? c : a.first + tile * 32;
     uint8_t* og = a.opt + cr * a.stride_o;
     uint8_t* pg = a.prio + cr * a.stride_p;
-    // both rows stream through registers, with the proposed move patched into the chunks
-    auto evaluate = [&](const PosMove& mv) -> float {
-      st.reset(a.nodes);
+    // both rows stream through registers, with the proposed move patched into the chunks.  Incremental
+    // rounds: `oc0` > 0 resumes at that 32-position block from the snapshot in front of it (buffer bit of
+    // `par`), `save` stores the state in front of every later window boundary into the other buffer
+    // (see SearchFuse::snap; a window is `wblk` blocks, chosen so that there are at most 32 windows).
+    auto evaluate = [&](const PosMove& mv, int oc0, uint32_t par, bool save, float* snap_t, int wblk) -> float {
       const int nout = (J + 31) / 32;  // outer iterations of 32 positions
-      PrioChunk qo = ld_prio32<false>(og);
+      if (oc0 == 0) {
+        st.reset(a.nodes);
+      } else {
+        const int b = oc0 / wblk - 1;
+        const float* sp = snap_t + ((b * 2 + ((par >> b) & 1u)) * 9) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st.f[i] = __ldcg(sp + i * 32);
+        st.mk = __ldcg(sp + 8 * 32);
+        st.pend = 0.f;
+      }
+      PrioChunk qo = ld_prio32<false>(og + oc0 * 32);
       PrioChunk qp[PCH];
 #pragma unroll
-      for (int h = 0; h < PCH; ++h) qp[h] = ld_prio32<false>(pg + h * 32);
-      for (int oc = 0; oc < nout; ++oc) {
+      for (int h = 0; h < PCH; ++h) qp[h] = ld_prio32<false>(pg + (oc0 * PCH + h) * 32);
+      for (int oc = oc0; oc < nout; ++oc) {
+        if (save && oc > oc0 && oc % wblk == 0) {
+          const int b = oc / wblk - 1;
+          float* sp = snap_t + ((b * 2 + (((par >> b) & 1u) ^ 1u)) * 9) * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) __stcg(sp + i * 32, st.f[i]);
+          __stcg(sp + 8 * 32, fmaxf(st.mk, st.pend));
+        }
         PrioChunk no = qo, np[PCH];
 #pragma unroll
         for (int h = 0; h < PCH; ++h) np[h] = qp[h];
@@ -461,7 +512,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     PosMove none;
     none.kind = 0; none.a = none.b = none.va = none.vb = none.oa = none.ob = 0;
     if (a.eval_only) {
-      const float mk = evaluate(none);
+      const float mk = evaluate(none, 0, 0u, false, nullptr, 1);
       if (active) a.sf.cur_mk[c] = mk;
       if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
       continue;
@@ -471,12 +522,43 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     float cm = active ? a.sf.cur_mk[c] : 0.f;
     bool moving = active;  // false from the round in which this lane lowers the global best key
     const uint64_t gid = a.sf.chain_base + static_cast<uint64_t>(c);
+    // incremental rounds (one node): windows of wblk 32-position blocks, at most 32 of them
+    const int nout_all = (J + 31) / 32;
+    const int wblk = (nout_all + 31) / 32;
+    const int nwin = (nout_all + wblk - 1) / wblk;
+    const bool win = !MULTI && a.sf.win != 0 && nwin >= 2;
+    const bool inc = win && a.sf.snap != nullptr;
+    float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
+    uint32_t par = 0;
+    if (inc) (void)evaluate(none, 0, ~0u, true, snap_t, wblk);  // unmodified pass: buffer 0 of every boundary
 #pragma unroll 1
     for (int r = 0; r < a.sf.nrounds; ++r) {
       const int round = a.sf.round + r;
+      int w0 = 0;
+      if (win) {
+        const uint64_t wr = rng_u64(a.sf.seed ^ 0x31d0ull, a.sf.chain_base + static_cast<uint64_t>(a.first + tile * 32),
+                                    static_cast<uint64_t>(round));
+        w0 = static_cast<int>(bounded(wr, nwin));
+      }
       PosMove mv = none;
-      if (moving) mv = make_pos_move<PB>(a.sf, round, J, gid, og, pg);
-      float mk = evaluate(mv);
+      if (moving) {
+        if (win) {
+          const int p0 = w0 * wblk * 32;
+          mv = make_pos_move_win<PB>(a.sf, round, J, gid, og, pg, p0, min(wblk * 32, J - p0));
+        } else {
+          mv = make_pos_move<PB>(a.sf, round, J, gid, og, pg);
+        }
+      }
+      float mk;
+      if (inc) {
+        mk = evaluate(mv, w0 * wblk, par, true, snap_t, wblk);
+        if (a.sf.verify_bad != nullptr) {
+          const float full = evaluate(mv, 0, par, false, snap_t, wblk);
+          if (active && __float_as_uint(full) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
+        }
+      } else {
+        mk = evaluate(mv, 0, 0u, false, nullptr, 1);
+      }
       if (moving) {
         bool acc = mk <= cm;
         const float temp = a.sf.temperature[r];
@@ -496,6 +578,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
           }
           a.sf.cur_mk[c] = mk;
           cm = mk;
+          if (inc) par ^= (w0 + 1 < nwin) ? (~0u << w0) : 0u;  // the boundary states this proposal wrote are current now
         } else if (!acc) {
           mk = cm;
         }

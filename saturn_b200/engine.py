@@ -233,10 +233,11 @@ class Engine:
     def search_init(self, chains: int, seed: int = 0, chain_base: int = 0, integer_starts: bool = True,
                     reduced: bool = False, t_start: float = 0.02, t_end: float = 1e-4, total_rounds: int = 200,
                     warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, resample_every: int = 0,
-                    _no_fused: bool = False):
-        """resample_every > 0: search_round resamples the population by tournament on that cadence itself."""
+                    _no_fused: bool = False, _extra_flags: int = 0):
+        """resample_every > 0: search_round resamples the population by tournament on that cadence itself.
+        _extra_flags: test hooks of sb_search_params.flags (see sb_search_verify_count in the header)."""
         p = SearchParams(seed=seed, chains=chains, chain_base=chain_base, resample_every=int(resample_every or 0),
-                         flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
+                         flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0) | int(_extra_flags),
                          t_start=t_start, t_end=t_end, total_rounds=total_rounds)
         wo = wp = None
         keep = None
@@ -258,12 +259,13 @@ class Engine:
                    reduced: bool = False, t_start: float = 5e-4, t_end: float = 1e-6,
                    warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, resample_every: int = -1, sync_every: int = 16,
                    patience: int = 0, time_budget_s: float = 0.0, target_makespan: float = 0.0,
-                   heuristic_seeds: bool = True, record_history: bool = False, _no_fused: bool = False):
+                   heuristic_seeds: bool = True, record_history: bool = False, _no_fused: bool = False,
+                   _extra_flags: int = 0):
         """The whole single-GPU search in one C call (sb_search_run).  Returns a dict: opt, prio, makespan, key,
         evaluated, rounds, stop_reason, wall_s, history [(wall s, evaluated, makespan)]."""
         return _search_run(self._lib, [self._h], self.J, chains, rounds, seed, chain_base, integer_starts, reduced,
                            t_start, t_end, warm, resample_every, sync_every, patience, time_budget_s, target_makespan,
-                           heuristic_seeds, record_history, _no_fused)
+                           heuristic_seeds, record_history, _no_fused, _extra_flags)
 
     def search_wave(self, reduced: bool = False) -> int:
         """Chains that fill the device exactly once with the round kernel of the current table; populations
@@ -303,6 +305,12 @@ class Engine:
     def search_resample(self):
         check(self._lib.sb_search_resample(self._h))
 
+    def search_verify_count(self) -> int:
+        """Incremental scores that differed from a from-scratch score (test hook, needs _extra_flags 0x08000000)."""
+        n = C.c_uint64(0)
+        check(self._lib.sb_search_verify_count(self._h, C.byref(n)))
+        return int(n.value)
+
     def search_validate(self) -> int:
         """Chains of the current population whose rows are not a permutation + existing table cells."""
         bad = C.c_int64(0)
@@ -317,11 +325,11 @@ class Engine:
 
 def _search_run(lib, handles, J, chains, rounds, seed, chain_base, integer_starts, reduced, t_start, t_end, warm,
                 resample_every, sync_every, patience, time_budget_s, target_makespan, heuristic_seeds,
-                record_history, _no_fused):
+                record_history, _no_fused, _extra_flags=0):
     """sb_search_run (one handle) / sb_search_run_multi (one handle per device of this process)."""
     pdt = np.uint8 if J <= 256 else np.uint16
     p = SearchParams(seed=seed, chains=chains, chain_base=chain_base,
-                     flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0),
+                     flags=_flags(integer_starts, reduced) | (0x20000000 if _no_fused else 0) | int(_extra_flags),
                      t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1))
     cap = (max(rounds, 1) // max(1, sync_every) + 3) if record_history else 0
     hw, he, hm = np.zeros(cap, np.float64), np.zeros(cap, np.int64), np.zeros(cap, np.float32)
@@ -404,11 +412,11 @@ class MultiEngine:
                    reduced: bool = False, t_start: float = 5e-4, t_end: float = 1e-6, warm=None,
                    resample_every: int = -1, sync_every: int = 16, patience: int = 0, time_budget_s: float = 0.0,
                    target_makespan: float = 0.0, heuristic_seeds: bool = True, record_history: bool = False,
-                   _no_fused: bool = False):
+                   _no_fused: bool = False, _extra_flags: int = 0):
         """`chains` is per device; the result's `evaluated` counts every device."""
         return _search_run(self._lib, [e._h for e in self.engines], self.J, chains, rounds, seed, chain_base,
                            integer_starts, reduced, t_start, t_end, warm, resample_every, sync_every, patience,
-                           time_budget_s, target_makespan, heuristic_seeds, record_history, _no_fused)
+                           time_budget_s, target_makespan, heuristic_seeds, record_history, _no_fused, _extra_flags)
 
 
 class _CudaArrayView:

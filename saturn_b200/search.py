@@ -77,7 +77,8 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
                warm: Optional[Tuple[np.ndarray, np.ndarray]] = None, use_dist: bool = True,
                target_makespan: Optional[float] = None, reseed_every: int = 0, resample_every: Optional[int] = None,
                record_history: bool = False, heuristic_seeds: bool = True,
-               exchange_every: int = 16, _no_fused: bool = False, _python_driver: bool = False) -> SearchResult:
+               exchange_every: int = 16, _no_fused: bool = False, _python_driver: bool = False,
+               _extra_flags: int = 0) -> SearchResult:
     """Run the search on `engine` (table already set).  Returns the best candidate found by any rank.
 
     `rounds` device rounds are issued in groups of `exchange_every` (tournament resampling every
@@ -93,7 +94,7 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
                               t_start=t_start, t_end=t_end, warm=warm, resample_every=resample_every,
                               sync_every=exchange_every, patience=patience or 0, time_budget_s=time_budget_s or 0.0,
                               target_makespan=target_makespan or 0.0, heuristic_seeds=heuristic_seeds,
-                              record_history=record_history, _no_fused=_no_fused)
+                              record_history=record_history, _no_fused=_no_fused, _extra_flags=_extra_flags)
         return SearchResult(opt=r["opt"], prio=r["prio"], makespan=r["makespan"], evaluated=r["evaluated"],
                             rounds=r["rounds"], wall_s=r["wall_s"], history=r["history"], owner_rank=0)
     rank = dist.get_rank() if dist else 0
@@ -103,7 +104,8 @@ def run_search(engine: Engine, chains: int = 1 << 16, rounds: int = 200, seed: i
     t0 = time.perf_counter()
     engine.search_init(chains, seed=seed, chain_base=rank * chains, integer_starts=integer_starts,
                        reduced=reduced, t_start=t_start, t_end=t_end, total_rounds=max(rounds, 1), warm=warm,
-                       resample_every=resample_every, **({"_no_fused": True} if _no_fused else {}))
+                       resample_every=resample_every, **({"_no_fused": True} if _no_fused else {}),
+                       **({"_extra_flags": _extra_flags} if _extra_flags else {}))
     if heuristic_seeds:
         # every rank plants the longest-processing-time seeds in an eighth of its population each;
         # the rest stays random (diversity), tournament resampling then concentrates the population

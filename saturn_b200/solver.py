@@ -190,17 +190,25 @@ def _engine(devices=None):
     return _MULTI[devices]
 
 
-def _check_horizon(T):
+def _check_horizon(T, found_makespan=None):
     """The kernels keep schedule times in fp32: `start + ceil(rt)` is exact only below 2^24 s (194 days).
-    A table whose worst-case serial schedule can cross that bound would silently lose the integer-start and
-    no-overlap properties of the emitted plan, so it is refused here (rescale to coarser time units)."""
-    finite = np.where(np.isfinite(T), T, 0.0).astype(np.float64)
-    horizon = float(np.ceil(finite.reshape(T.shape[0], -1).max(axis=1)).sum())
-    if horizon >= FP32_EXACT_HORIZON:
-        raise SolverError("sum of the tasks' longest runtimes is %.3g s >= 2^24 s: schedule times are not exact in "
+    Before the search: a table whose area lower bound (sum_j min_k k * rt_jk / 8) already reaches that bound
+    cannot have an exactly representable plan and is refused.  After the search (`found_makespan`, the
+    device's value): every time inside the winning schedule is <= its makespan, and fp32 addition rounds
+    monotonically, so a makespan below 2^24 proves that all of its starts were computed exactly; anything
+    else is refused instead of returned with silently rounded starts (rescale to coarser time units)."""
+    if found_makespan is not None:
+        if not float(found_makespan) < FP32_EXACT_HORIZON:
+            raise SolverError("best plan found has makespan %.6g s >= 2^24 s: its start times are not exact in "
+                              "fp32; express runtimes in coarser units (e.g. minutes)" % float(found_makespan))
+        return
+    k = np.arange(1, T.shape[-1] + 1, dtype=np.float64)
+    area = np.where(np.isfinite(T), T.astype(np.float64) * k, np.inf).reshape(T.shape[0], -1).min(axis=1)
+    lower = float(area.sum()) / NSLOT
+    if lower >= FP32_EXACT_HORIZON:
+        raise SolverError("area lower bound of the makespan is %.3g s >= 2^24 s: schedule times are not exact in "
                           "fp32 at that horizon; express runtimes in coarser units (e.g. minutes) or drop sentinel "
-                          "options" % horizon)
-
+                          "options" % lower)
 
 def _default_nodes() -> int:
     env = os.environ.get("SATURN_B200_NODES")
@@ -277,6 +285,7 @@ def solve(task_list, presolved=None, gurobi=True, threads=max(1, (os.cpu_count()
     warm = candidate_from_arrays(task_list, presolved, nodes)
     res = run_search(eng, chains=chains, rounds=rounds, seed=seed, integer_starts=integer_starts, reduced=True,
                      time_budget_s=budget, patience=max(40, rounds // 4), warm=warm)
+    _check_horizon(Tdev, res.makespan)
     dec = eng.decode(res.opt, res.prio, integer_starts=integer_starts, reduced=True)
     gpus = dec["gpus"].astype(np.int64)
     chosen = optindex[np.arange(J), gpus - 1]
@@ -438,6 +447,7 @@ def solve_table(T, mask=None, gcount=None, presolved=None, interval=1000, timeou
         warm = candidate_from_arrays([_Opt] * J, presolved, nodes)
     res = run_search(eng, chains=chains, rounds=rounds, seed=seed, integer_starts=integer_starts, reduced=True,
                      time_budget_s=budget, patience=max(40, rounds // 4), warm=warm)
+    _check_horizon(Tdev, res.makespan)
     dec = eng.decode(res.opt, res.prio, integer_starts=integer_starts, reduced=True)
     gpus = dec["gpus"].astype(np.int64)
     chosen = np.array([col_of_k[int(k)] for k in gpus], dtype=np.int64)

@@ -366,3 +366,31 @@ def test_initial_population_rows_are_valid(engine, J, nodes):
     engine.search_init(chains, seed=10, chain_base=17, reduced=True)
     assert engine.search_best()[3] != key1
     engine.set_table(T)
+
+
+@pytest.mark.parametrize("J", [256, 100, 300, 40, 700, 1024, 2100])
+def test_incremental_rounds_equal_full_evaluation(engine, J):
+    """Round 2: fused rounds score a proposal from the state snapshotted in front of the warp's window.
+    (a) with the verify hook every incremental score is recomputed from position 0 on the device: none differs;
+    (b) the search with snapshots and the search that scores the same windowed moves from position 0 walk
+        the same chains: identical incumbent key, rows and history under a fixed seed;
+    (c) the incumbent re-scores to its makespan in the oracle.
+    J = 700 and up run the position-major kernel (both rows streamed; windows of whole 32-position blocks)."""
+    from saturn_b200.search import run_search
+    T, valid = R.synth_table(J, 3, 8, seed=100 + J)
+    engine.set_table(T)
+    kw = dict(chains=9472, rounds=48, seed=11, reduced=True, use_dist=False, record_history=True, exchange_every=8)
+    a = run_search(engine, _extra_flags=0x08000000, **kw)
+    assert engine.search_verify_count() == 0
+    b = run_search(engine, _extra_flags=0x10000000, **kw)
+    c = run_search(engine, **kw)
+    for x in (b, c):
+        assert x.makespan == a.makespan and np.array_equal(x.opt, a.opt) and np.array_equal(x.prio, a.prio)
+        assert [h[2] for h in x.history] == [h[2] for h in a.history]
+    tab = R.canon_table(T, range(1, 9))
+    tmin, _ = R.reduce_table(tab)
+    assert float(R.list_schedule(tmin[:, None, :], c.opt, c.prio, True, np.float32)[0]) == c.makespan
+    assert c.history[-1][2] < c.history[0][2] or J <= 40
+    # the round-1 move generator (no windows) reaches a comparable plan: the windows cost no quality
+    d = run_search(engine, _extra_flags=0x04000000, **kw)
+    assert c.makespan <= d.makespan * 1.01

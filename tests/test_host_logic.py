@@ -361,9 +361,12 @@ def test_dense_table_from_trials_matches_the_profiler_reduction():
 def test_fp32_horizon_guard():
     """Schedule times are exact integers in fp32 only below 2^24 s: a table that can cross it is refused."""
     from saturn_b200.solver import SolverError, _check_horizon
-    T = np.full((20, 1, 8), np.inf, dtype=np.float32)
-    T[:, 0, 0] = 1.0e6
+    T = np.full((200, 1, 8), np.inf, dtype=np.float32)
+    T[:, 0, 0] = 1.0e6                     # 200 jobs of 1e6 s on one GPU each: area bound 2.5e7 s > 2^24
     with pytest.raises(SolverError):
         _check_horizon(T)
     T[:, 0, 0] = 36000.0
     _check_horizon(T)
+    _check_horizon(T, found_makespan=1.5e7)
+    with pytest.raises(SolverError):
+        _check_horizon(T, found_makespan=float(1 << 24))
