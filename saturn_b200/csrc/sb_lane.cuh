@@ -29,7 +29,11 @@ __device__ __forceinline__ PrioChunk ld_prio32(const uint8_t* p) {
 }
 
 // Per-lane evaluation state + the per-job step.
-template <bool INT, bool MULTI>
+// ADDR = 1 (shared-memory table and opt rows only): the two look-up addresses of a step are formed with
+// `mad.lo` on run-time multipliers, which ptxas must issue as IMAD on the FMA pipe instead of IADD3 / LEA on
+// the ALU pipe — the step is bound by the ALU pipe (half rate) and by issue together, so the same instruction
+// count with two fewer ALU instructions is the cheaper mix (profiles/r02_summary.md).
+template <bool INT, bool MULTI, int ADDR = 0>
 struct LaneState {
   float f[8];
   float mk;
@@ -38,6 +42,7 @@ struct LaneState {
   const float* tab;     // runtime table (shared memory or global)
   int SG;
   int one;
+  uint32_t orow_s, tab_s, four;  // ADDR = 1: shared-window addresses of orow / tab, and a run-time 4
   float4* ns;  // MULTI: lane-private node-state column; node n lives at ns[(2n)*32], ns[(2n+1)*32]
   int cur;     // MULTI: the node whose state is currently in f[] (its shared-memory copy is stale)
 
@@ -82,6 +87,17 @@ struct LaneState {
     }
   }
   __device__ __forceinline__ void step(int j, int ph = -1) {
+    if (!MULTI && ADDR == 1) {
+      uint32_t oa, o, idx, ta;
+      float rt;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(oa) : "r"(j), "r"(one), "r"(orow_s));
+      asm("ld.shared.u8 %0, [%1];" : "=r"(o) : "r"(oa));
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(idx) : "r"(j), "r"(SG), "r"(o));
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ta) : "r"(idx), "r"(four), "r"(tab_s));
+      asm("ld.shared.f32 %0, [%1];" : "=f"(rt) : "r"(ta));
+      ls_step<INT>(f, mk, pend, rt, static_cast<int>(o & 7u), one, ph);
+      return;
+    }
     const int o = orow[j];
     if (!MULTI) {
       const float rt = tab[j * SG + o];

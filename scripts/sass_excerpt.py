@@ -74,8 +74,9 @@ def main():
               len(fns), len(allins), hist["UBLKCP"], hist["SYNCS"], "LDG.*.256", full["LDG.*.256 (256-bit global loads)"],
               hist["FMNMX3"], hist["R2P"],
               sum(hist[k] for k in hist if k in ("HMMA", "IMMA", "UTCHMMA", "UTCQMMA", "QGMMA", "UTCIMMA", "BMMA"))))
-    want = [("_ZN2sb12k_eval_tilesILi1ELb1ELb1ELb0ELb0ELb0EEEvNS_8TileArgsE", "the measured kernel (bench `value`): C4, integer starts, prio streamed", 32),
-            ("_ZN2sb12k_eval_tilesILi1ELb1ELb0ELb0ELb1ELb0EEEvNS_8TileArgsE", "fused search round (solve()): rows in shared memory, incremental scoring", 16),
+    want = [("_ZN2sb12k_eval_tilesILi1ELb1ELb1ELb0ELb0ELb0ELi1EEEvNS_8TileArgsE", "the measured kernel (bench `value`): C4, integer starts, prio streamed, look-up addresses on the FMA pipe", 32),
+            ("_ZN2sb12k_eval_tilesILi1ELb1ELb1ELb0ELb0ELb0ELi0EEEvNS_8TileArgsE", "the same kernel with plain C++ addressing (test hook 0x02000000; the round-1 form)", 32),
+            ("_ZN2sb12k_eval_tilesILi1ELb1ELb0ELb0ELb1ELb0ELi0EEEvNS_8TileArgsE", "fused search round (solve()): rows in shared memory, incremental scoring", 16),
             ("_ZN2sb12k_search_posILi2ELb1ELb0EEEvNS_7PosArgsE", "position-major search round (J > ~450, u16 priorities)", 32)]
     for name, what, steps in want:
         if name not in fns:

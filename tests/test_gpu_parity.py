@@ -68,6 +68,10 @@ def test_all_kernel_paths_agree(engine):
     a2 = engine.eval(opt, prio, _no_stream=True)
     assert engine.last_eval_path() == 2
     assert torch.equal(a, a2)
+    for ints in (True, False):            # the streaming kernel with and without the FMA-pipe address form
+        x = engine.eval(opt, prio, integer_starts=ints)
+        y = engine.eval(opt, prio, integer_starts=ints, _plain_addr=True)
+        assert engine.last_eval_path() == 3 and torch.equal(x, y)
     opt_u = opt.contiguous()              # row stride J = 100 bytes: not 16-byte aligned
     prio_u = prio.contiguous()
     b = engine.eval(opt_u, prio_u)
