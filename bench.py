@@ -45,8 +45,9 @@ METRIC = "candidate schedules/sec"
 UNIT = "candidates/s"
 J, S, G = 256, 8, 8
 WORKLOAD = "C4: J=256 jobs x S=8 strategies x G=1..8 GPUs, synthetic T (seed 0), integer starts"
-WAVE = 148 * 8 * 32           # candidates in one full wave of 32-candidate tiles (148 SMs x 8 warps)
-B_PER_GPU = WAVE * 27         # 1,022,976 candidates = 528 MB of encodings per step (> 126 MB L2)
+WAVE = 148 * 8 * 32           # candidates in one half wave of 32-candidate tiles (148 SMs x 16 resident warps / 2)
+B_PER_GPU = WAVE * 28         # 1,060,864 candidates = 14 whole tiles for every resident warp of the persistent
+                              # grid (no idle warps in a last partial wave) = 543 MB of encodings per step (> 126 MB L2)
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -279,7 +280,7 @@ def main():
         WORKLOAD = "%s: J=%d jobs x S=%d strategies x G=1..%d GPUs, synthetic T (diagnostic, not the headline)" % (
             args.config, J, S, G)
         if args.batch == B_PER_GPU:
-            args.batch = max(WAVE, (B_PER_GPU * 256 // J) // WAVE * WAVE)
+            args.batch = max(2 * WAVE, (B_PER_GPU * 256 // J) // (2 * WAVE) * (2 * WAVE))
     T, valid = synth_table(J, S, G, seed=0)
     if args.reduced:
         T = np.where(valid, T, np.inf).min(axis=1, keepdims=True).astype(np.float32)
@@ -518,7 +519,7 @@ def main():
             else:
                 eng.set_table(Tc)
                 valid_c = vc
-            Bc = max(WAVE, (B_PER_GPU * 256 // Jc) // WAVE * WAVE)
+            Bc = max(2 * WAVE, (B_PER_GPU * 256 // Jc) // (2 * WAVE) * (2 * WAVE))      # whole waves of 16 warps per SM
             oc, pc = random_candidates(eng, Bc, valid_c, seed=11)
             if by_pos:
                 oc = opt_by_position(oc, pc)

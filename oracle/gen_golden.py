@@ -222,6 +222,15 @@ def main_extra():
     (run offline, several instances side by side) -> tests/golden/milp_cases_extra.json."""
     import multiprocessing as mp
     jobs = []
+    if "--part2" in sys.argv:
+        # instances of the sizes HiGHS closes to a zero gap within minutes: more proven optima for H6
+        for seed in range(50, 62):
+            jobs.append(("H4_hetero_seed%d" % seed, hetero_tuples(4, seed), 420))
+        for i, opts in enumerate(([1, 2], [2, 4], [4, 8], [2, 8], [1, 8], [1, 4])):
+            jobs.append(("J4_g%s_seed%d" % ("".join(map(str, opts)), 70 + i), probe_tuples(4, opts, 70 + i), 420))
+        for i, opts in enumerate(([8], [4, 8], [2, 8])):
+            jobs.append(("J5_g%s_seed%d" % ("".join(map(str, opts)), 80 + i), probe_tuples(5, opts, 80 + i), 420))
+        return _run_extra(jobs, "milp_cases_extra2.json", "--extra --part2")
     for seed in range(21, 29):
         jobs.append(("H4_hetero_seed%d" % seed, hetero_tuples(4, seed), 600))
     for seed in range(31, 39):
@@ -236,12 +245,17 @@ def main_extra():
         ("J5_g1248_seed9", probe_tuples(5, [1, 2, 4, 8], 9), 900),
         ("J5_g124_seed10", probe_tuples(5, [1, 2, 4], 10), 900),
     ]
+    return _run_extra(jobs, "milp_cases_extra.json", "--extra")
+
+
+def _run_extra(jobs, fname, how):
+    import multiprocessing as mp
     workers = int(os.environ.get("GEN_GOLDEN_WORKERS", "6"))
     with mp.get_context("spawn").Pool(workers) as pool:
         recs = pool.map(_extra_worker, jobs, chunksize=1)
-    out = {"generator": "oracle/gen_golden.py --extra", "reference_commit": "b65e3d2",
+    out = {"generator": "ORACLE_MIP_REL_GAP=0 oracle/gen_golden.py " + how, "reference_commit": "b65e3d2",
            "scipy": __import__("scipy").__version__, "cases": recs}
-    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "milp_cases_extra.json")
+    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", fname)
     with open(dst, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", dst, "proven optimal:", sum(r["proven_optimal"] for r in recs), "of", len(recs))

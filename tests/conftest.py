@@ -37,8 +37,8 @@ def golden():
         d = json.load(f)
     # round 2: more instances recorded from the unmodified reference (oracle/gen_golden.py --extra, HiGHS run
     # to a zero gap): heterogeneous J = 4..5 and J = 6 — same record layout, so every golden test covers them
-    extra = os.path.join(ROOT, "tests", "golden", "milp_cases_extra.json")
-    if os.path.exists(extra):
+    import glob
+    for extra in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "milp_cases_extra*.json"))):
         with open(extra) as f:
             d = dict(d, cases=d["cases"] + json.load(f)["cases"])
     return d
