@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       const int J = a.J;
       constexpr int STEPS = 16 / PB;            // schedule positions per 128-bit shared-memory read
       constexpr int CPW = kSnapPos / STEPS;     // reads per window
-      const int nwin = (J + kSnapPos - 1) / kSnapPos;
+      const int nch = (J + STEPS - 1) / STEPS;
       if (w0 == 0) {
         st.reset(a.nodes);
       } else {
@@ -239,30 +239,28 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         st.pend = 0.f;
       }
       const uint4* prow = reinterpret_cast<const uint4*>(prio_row_s);
+      // ONE copy of the unrolled step body in this loop: the kernel is instruction-fetch bound as soon as the
+      // hot path spans several unrolled bodies (the first version, a window loop around CPW unrolled reads and
+      // three inlined call sites, ran at 29 % issue-active with 6.9 "no instruction" stalls per issue,
+      // profiles/r02_search_inc_v1_raw.csv)
 #pragma unroll 1
-      for (int w = w0; w < nwin; ++w) {
-        if (save && w > w0) {
-          float* sp = snap_t + (((w - 1) * 2 + (((par >> (w - 1)) & 1u) ^ 1u)) * 9) * 32 + lane;
+      for (int c = w0 * CPW; c < nch; ++c) {
+        if (save && c > w0 * CPW && (c % CPW) == 0) {
+          const int b = c / CPW - 1;  // boundary in front of window b + 1
+          float* sp = snap_t + ((b * 2 + (((par >> b) & 1u) ^ 1u)) * 9) * 32 + lane;
 #pragma unroll
           for (int i = 0; i < 8; ++i) __stcg(sp + i * 32, st.f[i]);
           __stcg(sp + 8 * 32, fmaxf(st.mk, st.pend));
         }
+        const uint4 p = prow[c];
+        const uint32_t wd[4] = {p.x, p.y, p.z, p.w};
+        if ((c + 1) * STEPS <= J) {
 #pragma unroll
-        for (int cc = 0; cc < CPW; ++cc) {
-          const int c = w * CPW + cc;
-          if (c * STEPS < J) {
-            const uint4 p = prow[c];
-            const uint32_t wd[4] = {p.x, p.y, p.z, p.w};
-            if ((c + 1) * STEPS <= J) {
-#pragma unroll
-              for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(wd, t), t & 1);
-            } else {
-              const int rem = J - c * STEPS;
-#pragma unroll
-              for (int t = 0; t < STEPS; ++t)
-                if (t < rem) st.step(prio_at<PB>(wd, t), t & 1);
-            }
-          }
+          for (int t = 0; t < STEPS; ++t) st.step(prio_at<PB>(wd, t), t & 1);
+        } else {
+          const int rem = J - c * STEPS;
+#pragma unroll 1
+          for (int t = 0; t < rem; ++t) st.step(PB == 1 ? prio_row_s[c * STEPS + t] : reinterpret_cast<const uint16_t*>(prio_row_s)[c * STEPS + t], -1);
         }
       }
       return st.result();
@@ -295,13 +293,13 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       const int nwin = (a.J + kSnapPos - 1) / kSnapPos;
       float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
       uint32_t par = 0;  // bit w-1: which buffer holds the current candidate's state in front of window w
-      if (inc) {
-        (void)eval_from(prow_s, 0, ~0u, true, snap_t);  // writes buffer 0 of every boundary
-      }
+      // r = -1 (incremental only) is the unmodified pass that fills buffer 0 of every boundary; it shares the
+      // one call site of eval_from with the rounds
 #pragma unroll 1
-      for (int r = 0; r < a.sf.nrounds; ++r) {
+      for (int r = inc ? -1 : 0; r < a.sf.nrounds; ++r) {
         const int round = a.sf.round + r;
-        if (a.sf.resample_every > 0 && round > 1 && (round - 1) % a.sf.resample_every == 0) {
+        const bool fill = r < 0;
+        if (!fill && a.sf.resample_every > 0 && round > 1 && (round - 1) % a.sf.resample_every == 0) {
           // tournament inside the warp: take over the rows of a random lane if its candidate is better.
           // Rows move 16 bytes at a time through registers, every lane reading chunk i before any lane
           // writes chunk i, so a lane that is both source and taker is still copied in its old state.
@@ -327,19 +325,33 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
             __syncwarp();
           }
           if (inc) {
-            // ... and its boundary snapshots: word by word from the rival's current buffers into this lane's
-            // current buffers (same read-all-then-write discipline)
+            // ... and its boundary snapshots, from the rival's current buffers into this lane's current buffers.
+            // ALL loads of a batch (up to 7 boundaries = 63 words; the evaluation registers are free here) are
+            // issued before the first store, so a tournament costs one trip to L2 / HBM per batch, not one per
+            // boundary (the first version copied boundary by boundary: 7 dependent round trips every other round
+            // made the incremental kernel 2x SLOWER than scoring from position 0, profiles/r02_incremental.md).
             const uint32_t rpar = __shfl_sync(0xffffffffu, par, rival);
-            for (int b = 0; b < nwin - 1; ++b) {
-              const float* src = snap_t + ((b * 2 + ((rpar >> b) & 1u)) * 9) * 32 + rival;
-              float* dst = snap_t + ((b * 2 + ((par >> b) & 1u)) * 9) * 32 + lane;
-              float v[9];
+            constexpr int kBatch = 7;
+            for (int b0s = 0; b0s < nwin - 1; b0s += kBatch) {
+              float v[kBatch][9];
 #pragma unroll
-              for (int i = 0; i < 9; ++i) v[i] = __ldcg(src + i * 32);
-              __syncwarp();
-              if (take) {
+              for (int bb = 0; bb < kBatch; ++bb) {
+                const int b = b0s + bb;
+                if (take && b < nwin - 1) {
+                  const float* src = snap_t + ((b * 2 + ((rpar >> b) & 1u)) * 9) * 32 + rival;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) __stcg(dst + i * 32, v[i]);
+                  for (int i = 0; i < 9; ++i) v[bb][i] = __ldcg(src + i * 32);
+                }
+              }
+              __syncwarp();  // every lane has read its rival's state of this batch before any lane overwrites its own
+#pragma unroll
+              for (int bb = 0; bb < kBatch; ++bb) {
+                const int b = b0s + bb;
+                if (take && b < nwin - 1) {
+                  float* dst = snap_t + ((b * 2 + ((par >> b) & 1u)) * 9) * 32 + lane;
+#pragma unroll
+                  for (int i = 0; i < 9; ++i) __stcg(dst + i * 32, v[bb][i]);
+                }
               }
               __syncwarp();
             }
@@ -351,14 +363,14 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         }
         // the window of this round: one draw per (warp's first chain, round), the same in all 32 lanes
         int w0 = 0;
-        if (win) {
+        if (win && !fill) {
           const uint64_t wr = rng_u64(a.sf.seed ^ 0x31d0ull, a.sf.chain_base + static_cast<uint64_t>(a.sf.deal ? tile : b0),
                                       static_cast<uint64_t>(round));
           w0 = static_cast<int>(bounded32(wr, nwin));
         }
         Move mv;
         mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = 0;
-        if (moving) {
+        if (moving && !fill) {
           if (win) {
             const int p0 = w0 * kSnapPos;
             mv = apply_move_win<PB>(a.sf, round, a.J, gid, orow_s, prow_s, p0, min(kSnapPos, a.J - p0));
@@ -367,16 +379,17 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
           }
         }
         __syncwarp();  // shadowing lanes read lane 0's rows
-        float mk;
-        if (inc) {
-          mk = eval_from(prow_s, w0, par, true, snap_t);
-          if (a.sf.verify_bad != nullptr) {
-            const float full = eval_from(prow_s, 0, par, false, snap_t);
-            if (active && __float_as_uint(full) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
-          }
-        } else {
-          mk = evaluate(prow_s);
+        // the one evaluation site: trip 0 is the round's score (resumed from the window's snapshot when
+        // incremental), trip 1 — verify hook only — recomputes it from position 0 and compares
+        float mk = 0.f;
+        const int trips = (inc && !fill && a.sf.verify_bad != nullptr) ? 2 : 1;
+#pragma unroll 1
+        for (int trip = 0; trip < trips; ++trip) {
+          const float got = eval_from(prow_s, (inc && trip == 0) ? w0 : 0, fill ? ~0u : par, inc && trip == 0, snap_t);
+          if (trip == 0) mk = got;
+          else if (active && __float_as_uint(got) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
         }
+        if (fill) continue;
         if (moving) {
           bool acc = mk <= cm;
           const float temp = a.sf.temperature[r];

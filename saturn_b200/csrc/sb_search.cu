@@ -511,37 +511,36 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     };
     PosMove none;
     none.kind = 0; none.a = none.b = none.va = none.vb = none.oa = none.ob = 0;
-    if (a.eval_only) {
-      const float mk = evaluate(none, 0, 0u, false, nullptr, 1);
-      if (active) a.sf.cur_mk[c] = mk;
-      if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
-      continue;
-    }
     // sf.nrounds rounds per launch: an accepted move is written to the rows, which the next round streams
-    // again; the lane that lowers the global best key stops moving (see k_eval_tiles)
-    float cm = active ? a.sf.cur_mk[c] : 0.f;
-    bool moving = active;  // false from the round in which this lane lowers the global best key
+    // again; the lane that lowers the global best key stops moving (see k_eval_tiles).  eval_only: one pass that
+    // scores the rows as they are.  The evaluation has ONE call site (the kernel becomes instruction-fetch
+    // bound when the unrolled 32-step body is inlined several times): the scoring pass of eval_only, the
+    // unmodified pass that fills the snapshots (r = -1), the rounds and the verify hook's recomputation all go
+    // through it.
+    float cm = (active && !a.eval_only) ? a.sf.cur_mk[c] : 0.f;
+    bool moving = active && !a.eval_only;  // false from the round in which this lane lowers the global best key
     const uint64_t gid = a.sf.chain_base + static_cast<uint64_t>(c);
     // incremental rounds (one node): windows of wblk 32-position blocks, at most 32 of them
     const int nout_all = (J + 31) / 32;
     const int wblk = (nout_all + 31) / 32;
     const int nwin = (nout_all + wblk - 1) / wblk;
-    const bool win = !MULTI && a.sf.win != 0 && nwin >= 2;
+    const bool win = !a.eval_only && !MULTI && a.sf.win != 0 && nwin >= 2;
     const bool inc = win && a.sf.snap != nullptr;
     float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
     uint32_t par = 0;
-    if (inc) (void)evaluate(none, 0, ~0u, true, snap_t, wblk);  // unmodified pass: buffer 0 of every boundary
+    const int r_end = a.eval_only ? 1 : a.sf.nrounds;
 #pragma unroll 1
-    for (int r = 0; r < a.sf.nrounds; ++r) {
+    for (int r = inc ? -1 : 0; r < r_end; ++r) {
       const int round = a.sf.round + r;
+      const bool fill = r < 0;  // unmodified pass: buffer 0 of every boundary
       int w0 = 0;
-      if (win) {
+      if (win && !fill) {
         const uint64_t wr = rng_u64(a.sf.seed ^ 0x31d0ull, a.sf.chain_base + static_cast<uint64_t>(a.first + tile * 32),
                                     static_cast<uint64_t>(round));
         w0 = static_cast<int>(bounded(wr, nwin));
       }
       PosMove mv = none;
-      if (moving) {
+      if (moving && !fill) {
         if (win) {
           const int p0 = w0 * wblk * 32;
           mv = make_pos_move_win<PB>(a.sf, round, J, gid, og, pg, p0, min(wblk * 32, J - p0));
@@ -549,17 +548,18 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
           mv = make_pos_move<PB>(a.sf, round, J, gid, og, pg);
         }
       }
-      float mk;
-      if (inc) {
-        mk = evaluate(mv, w0 * wblk, par, true, snap_t, wblk);
-        if (a.sf.verify_bad != nullptr) {
-          const float full = evaluate(mv, 0, par, false, snap_t, wblk);
-          if (active && __float_as_uint(full) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
-        }
-      } else {
-        mk = evaluate(mv, 0, 0u, false, nullptr, 1);
+      float mk = 0.f;
+      const int trips = (inc && !fill && a.sf.verify_bad != nullptr) ? 2 : 1;
+#pragma unroll 1
+      for (int trip = 0; trip < trips; ++trip) {
+        const float got = evaluate(mv, (inc && trip == 0) ? w0 * wblk : 0, fill ? ~0u : par, inc && trip == 0, snap_t, wblk);
+        if (trip == 0) mk = got;
+        else if (active && __float_as_uint(got) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
       }
-      if (moving) {
+      if (fill) continue;
+      if (a.eval_only) {
+        if (active) a.sf.cur_mk[c] = mk;
+      } else if (moving) {
         bool acc = mk <= cm;
         const float temp = a.sf.temperature[r];
         if (!acc && temp > 0.f && isfinite(mk)) {

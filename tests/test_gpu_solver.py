@@ -379,7 +379,9 @@ def test_incremental_rounds_equal_full_evaluation(engine, J):
     from saturn_b200.search import run_search
     T, valid = R.synth_table(J, 3, 8, seed=100 + J)
     engine.set_table(T)
-    kw = dict(chains=9472, rounds=48, seed=11, reduced=True, use_dist=False, record_history=True, exchange_every=8)
+    # an explicit tournament cadence: the automatic one differs between the modes for position-major populations
+    kw = dict(chains=9472, rounds=48, seed=11, reduced=True, use_dist=False, record_history=True, exchange_every=8,
+              resample_every=4)
     a = run_search(engine, _extra_flags=0x08000000, **kw)
     assert engine.search_verify_count() == 0
     b = run_search(engine, _extra_flags=0x10000000, **kw)
