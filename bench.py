@@ -123,7 +123,7 @@ def ncu_traffic():
     try:
         with open(p) as f:
             d = json.load(f)
-        return d.get("dram_bytes_per_launch"), d.get("algorithmic_bytes_per_launch")
+        return d.get("dram_bytes_per_launch"), d.get("candidates_per_launch")
     except Exception:
         return None, None
 
@@ -488,7 +488,7 @@ def main():
         eng.search_init(chains, seed=rank, chain_base=rank * chains, integer_starts=ints, reduced=True,
                         t_start=5e-4, t_end=1e-6, total_rounds=64)
         i1.record()
-        eng.search_round(8)
+        eng.search_round(16)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -497,10 +497,11 @@ def main():
         torch.cuda.synchronize()
         ms = s0.elapsed_time(s1) / 32
         search_leg = {"candidates_per_s_per_gpu": chains / (ms * 1e-3), "ms_per_round": ms, "chains_per_gpu": chains,
-                      "fused": eng.search_is_fused(), "rounds_per_launch": 8,
+                      "fused": eng.search_is_fused(), "rounds_per_launch": 16,
                       "init_ms": i0.elapsed_time(i1),
                       "what": "the round kernel solve() runs (min-over-strategies table): move + evaluate + Metropolis "
-                              "accept of every chain, 8 rounds per launch with the rows resident in shared memory; "
+                              "accept of every chain, scored incrementally from the snapshot in front of the warp's move window, 16 rounds per "
+                              "launch with the rows resident in shared memory; "
                               "init_ms = sb_search_init of that population (shuffle in shared memory + first scoring)"}
 
     # ---- the other BASELINE shapes, a fraction of a second each (diagnostic)
@@ -547,7 +548,9 @@ def main():
         peak, peak_src = measured_peak()
         alg = B * bytes_per_candidate(J)
         achieved = alg / (kern_ms_max * 1e-3) / 1e9
-        dram, _alg_ncu = ncu_traffic()
+        dram, ncu_batch = ncu_traffic()
+        if dram is not None and ncu_batch:                     # the capture's launch may be a different batch: per candidate
+            dram = int(round(dram * B / ncu_batch))
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": dram if headline else None, "eval_path": kernel_path,
                 "kernel": "k_eval_tiles<1,%s,true>" % ("true" if ints else "false"),

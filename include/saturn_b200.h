@@ -212,10 +212,11 @@ typedef struct sb_search_params {
 
 int sb_search_init(sb_handle* h, const sb_search_params* p, const uint8_t* warm_opt /*host, nullable*/,
                    const void* warm_prio /*host, nullable*/);
-/* `rounds` Metropolis rounds, asynchronous on the handle's stream.  Fused rounds are issued up to 8 per launch:
+/* `rounds` Metropolis rounds, asynchronous on the handle's stream.  Fused rounds are issued up to 16 per launch:
  * a warp keeps its 32 chains' rows on chip and runs the rounds back to back (a rejected move is undone in
- * place, an accepted one writes its few changed bytes through to HBM); the chain that lowers the best key stops
- * moving until the launch ends, so the saved incumbent is exactly the candidate the key was scored on. */
+ * place, an accepted one writes its few changed bytes through to HBM); a chain whose candidate beats the incumbent
+ * saved before the launch stops moving until the launch ends, so the saved incumbent is exactly the candidate
+ * its key was scored on — and a search is reproducible bit for bit whatever the interleaving of warps. */
 int sb_search_round(sb_handle* h, int rounds);
 /* device pointer to the uint64 best key ((makespan bits << 32) | global chain id) */
 int sb_search_best_key_ptr(sb_handle* h, uint64_t** key_dev);

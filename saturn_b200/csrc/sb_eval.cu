@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       // hot path spans several unrolled bodies (the first version, a window loop around CPW unrolled reads and
       // three inlined call sites, ran at 29 % issue-active with 6.9 "no instruction" stalls per issue,
       // profiles/r02_search_inc_v1_raw.csv)
-#pragma unroll 1
+#pragma unroll 2
       for (int c = w0 * CPW; c < nch; ++c) {
         if (save && c > w0 * CPW && (c % CPW) == 0) {
           const int b = c / CPW - 1;  // boundary in front of window b + 1
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       const int nwin = (a.J + kSnapPos - 1) / kSnapPos;
       float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
       uint32_t par = 0;  // bit w-1: which buffer holds the current candidate's state in front of window w
+      const uint32_t inc_bits = launch_incumbent_bits(a.sf);  // makespan of the incumbent saved before this launch
       // r = -1 (incremental only) is the unmodified pass that fills buffer 0 of every boundary; it shares the
       // one call site of eval_from with the rounds
 #pragma unroll 1
@@ -411,8 +412,8 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
             mk = cm;
           }
         }
-        if (a.best_key != nullptr && fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(c), lane))
-          moving = false;
+        if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(c), lane);
+        if (active && __float_as_uint(mk) < inc_bits) moving = false;  // see launch_incumbent_bits
       }
       st.orow = tile_o + lane * a.row_o;
     }

@@ -54,7 +54,7 @@ struct EvalCall {
 };
 
 // what the fused search round needs besides an EvalCall (see k_eval_tiles<..., SEARCH = true>)
-constexpr int kMaxFusedRounds = 8;
+constexpr int kMaxFusedRounds = 16;
 constexpr int kSnapPos = 32;  // schedule positions per window / between state snapshots (incremental search rounds)
 struct SearchFuse {
   float* cur_mk = nullptr;        // [chains] makespan of each chain's current candidate
@@ -66,7 +66,7 @@ struct SearchFuse {
   int round = 0;    // first round of this launch (RNG counters are keyed by the round number)
   int nrounds = 1;  // rounds run back to back inside one launch, the rows staying on chip (<= kMaxFusedRounds)
   int nodes = 1;
-  float temperature[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // per round of this launch
+  float temperature[kMaxFusedRounds] = {};  // per round of this launch
   // Tournament resampling inside the tile kernel: before every round r with (r - 1) % resample_every == 0
   // (r > 1) each lane takes over the rows of a random lane of its warp if that lane's candidate is better.
   // `deal` changes which chains share a warp: 0 = chain = tile * 32 + lane, 1 = chain = lane * ntiles + tile.

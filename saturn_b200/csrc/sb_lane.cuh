@@ -133,6 +133,18 @@ __device__ __forceinline__ bool fold_best(unsigned long long* best_key, bool act
   return lowered;
 }
 
+// Which chains stop moving inside a multi-round launch.  The tail below saves the rows of the chain that holds
+// the population's best key, so those rows must still be the candidate the key was scored on: a chain whose
+// candidate is strictly better than the incumbent saved BEFORE this launch (keys[1]; only the tail of a launch
+// writes it, after every CTA has finished) stops moving for the rest of the launch.  The rule reads nothing that
+// other warps write during the launch, so a search is reproducible bit for bit whatever the interleaving of
+// warps (the first version froze the chain that won the atomicMin race, which made runs depend on timing).
+__device__ __forceinline__ uint32_t launch_incumbent_bits(const SearchFuse& sf) {
+  return sf.keep.keys != nullptr
+             ? static_cast<uint32_t>(*reinterpret_cast<volatile unsigned long long*>(sf.keep.keys + 1) >> 32)
+             : 0u;
+}
+
 // Tail of a fused search round: every thread's accepted row bytes are fenced, the CTA that finishes last
 // has therefore seen the whole round; its first warp saves the incumbent's rows if keys[0] improved on
 // keys[1] (what k_keep_best does as a separate launch for the unfused rounds).
@@ -149,7 +161,8 @@ __device__ __forceinline__ void keep_best_tail(const SearchFuse& sf) {
   __threadfence();
   const int lane = threadIdx.x;
   const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(sf.keep.keys);
-  if (key >= *reinterpret_cast<volatile unsigned long long*>(sf.keep.keys + 1)) return;
+  // only a strictly better MAKESPAN replaces the saved incumbent: exactly the chains that froze (frozen_by)
+  if ((key >> 32) >= (*reinterpret_cast<volatile unsigned long long*>(sf.keep.keys + 1) >> 32)) return;
   const long long c = static_cast<long long>(((key & 0xffffffffull) - (sf.chain_base & 0xffffffffull)) & 0xffffffffull);
   if (c >= sf.keep.chains) return;
   const uint4* so = reinterpret_cast<const uint4*>(sf.cur_o + c * sf.keep.stride_o);

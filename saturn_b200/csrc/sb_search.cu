@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     const bool inc = win && a.sf.snap != nullptr;
     float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
     uint32_t par = 0;
+    const uint32_t inc_bits = a.eval_only ? 0u : launch_incumbent_bits(a.sf);
     const int r_end = a.eval_only ? 1 : a.sf.nrounds;
 #pragma unroll 1
     for (int r = inc ? -1 : 0; r < r_end; ++r) {
@@ -583,8 +584,8 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
           mk = cm;
         }
       }
-      if (a.best_key != nullptr && fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane))
-        moving = false;
+      if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
+      if (active && !a.eval_only && __float_as_uint(mk) < inc_bits) moving = false;  // see launch_incumbent_bits
     }
   }
   if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);

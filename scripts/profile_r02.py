@@ -18,8 +18,8 @@ WAVE = 148 * 8 * 32
 if which in ("eval", "eval_plain"):
     T, valid = synth_table(256, 8, 8, seed=0)
     eng.set_table(T)
-    opt, prio = random_candidates(eng, WAVE * 27, valid, seed=1)
-    out = torch.empty(WAVE * 27, dtype=torch.float32, device="cuda")
+    opt, prio = random_candidates(eng, WAVE * 28, valid, seed=1)    # the bench batch
+    out = torch.empty(WAVE * 28, dtype=torch.float32, device="cuda")
     for _ in range(5):
         eng.eval(opt, prio, out=out, _plain_addr=(which == "eval_plain"))
     torch.cuda.synchronize()
