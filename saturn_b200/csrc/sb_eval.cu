@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       // hot path spans several unrolled bodies (the first version, a window loop around CPW unrolled reads and
       // three inlined call sites, ran at 29 % issue-active with 6.9 "no instruction" stalls per issue,
       // profiles/r02_search_inc_v1_raw.csv)
-#pragma unroll 2
+#pragma unroll 1
       for (int c = w0 * CPW; c < nch; ++c) {
         if (save && c > w0 * CPW && (c % CPW) == 0) {
           const int b = c / CPW - 1;  // boundary in front of window b + 1

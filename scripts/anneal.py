@@ -2,6 +2,7 @@
 
     python scripts/anneal.py --config C5 --chains 262144 --candidates 1e9
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/anneal.py ...
+    python scripts/anneal.py --config C5 --devices 8 ...      # ONE process driving 8 devices (sb_search_run_multi)
 
 Prints the best-makespan-vs-time curve (rank 0) as a markdown table: the "1e9-candidate anneal on
 8xB200; makespan vs reference MILP wall-clock" item of BASELINE.json (the MILP column is "no
@@ -27,21 +28,25 @@ def main():
     ap.add_argument("--config", default="C5")
     ap.add_argument("--chains", type=int, default=1 << 18, help="per GPU")
     ap.add_argument("--candidates", type=float, default=1e9, help="total over all GPUs")
-    ap.add_argument("--exchange-every", type=int, default=4)
+    ap.add_argument("--exchange-every", type=int, default=16)
+    ap.add_argument("--devices", type=int, default=0, help="one process, this many devices (no torchrun)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         warm = torch.zeros(1, dtype=torch.int64, device="cuda")
         dist.all_reduce(warm, op=dist.ReduceOp.MIN)          # communicator set-up is not part of the anneal
     J, S, G, seed = CONFIGS[args.config]
     T, valid = synth_table(J, S, G, seed=seed)
-    eng = Engine(local)
+    if args.devices > 1:
+        from saturn_b200.engine import MultiEngine
+        eng = MultiEngine(args.devices)
+        world = args.devices                     # for the candidate budget below; `rank` stays 0
+    else:
+        eng = Engine(local)
     eng.set_table(T)
     tmin, _ = eng.reduced_table()
     usable = np.where(tmin < 1e6, tmin, np.inf)
@@ -50,11 +55,12 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = run_search(eng, chains=args.chains, rounds=rounds, seed=0, reduced=True, record_history=True,
-                     exchange_every=args.exchange_every)
+                     exchange_every=args.exchange_every, use_dist=args.devices <= 1)
     wall = time.perf_counter() - t0
     if rank == 0:
-        print("# %s anneal: J=%d, S=%d (min over strategies), G=1..%d; %d GPU(s) x %d chains x %d rounds\n" % (
-            args.config, J, S, G, world, args.chains, res.rounds))
+        print("# %s anneal: J=%d, S=%d (min over strategies), G=1..%d; %d GPU(s) x %d chains x %d rounds%s\n" % (
+            args.config, J, S, G, world, args.chains, res.rounds,
+            " (one process, sb_search_run_multi)" if args.devices > 1 else ""))
         print("candidates evaluated: %.3e in %.3f s  (%.3e candidates/s whole job); area lower bound %.1f\n" % (
             res.evaluated, wall, res.evaluated / wall, lb))
         print("| wall s | candidates | best makespan | gap to lower bound |\n|---|---|---|---|")
@@ -66,7 +72,7 @@ def main():
                 print("| %.3f | %.2e | %.1f | %.2f %% |" % (t, n, mk, 100 * (mk / lb - 1)))
         print("\nreference MILP on the same T: model of %d x %d tasks/options cannot be built (SURVEY §8a: 134 M rows "
               "at J=1024; HiGHS has no incumbent at J=24 after 30 s, profiles/r01_milp_vs_gpu.md)" % (J, 8))
-    if world > 1:
+    if world > 1 and args.devices <= 1:
         dist.destroy_process_group()
 
 
