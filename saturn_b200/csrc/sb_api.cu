@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <chrono>
 #include <new>
+#include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -63,6 +65,7 @@ struct sb_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int J = 0, S = 0;
+  int tab_J = 0, tab_S = 0;  // shape the table buffers are allocated for
   int nodes = 1;
   float sentinel = kSentinel;
   float* tab = nullptr;
@@ -83,6 +86,8 @@ struct sb_handle {
   // scratch for decode
   uint8_t* dec_buf = nullptr;
   size_t dec_cap = 0;
+  float* stage_T = nullptr;  // device staging of a host table (kept across sb_set_table calls)
+  size_t stage_T_bytes = 0;
   SearchState search;
   int last_path = -1;
   // peer-memory exchange
@@ -105,6 +110,7 @@ static void free_table(sb_handle* h) {
   for (int i = 0; i < 2; ++i) { cudaFree(h->vopt[i]); cudaFree(h->nvalid[i]); h->vopt[i] = nullptr; h->nvalid[i] = nullptr; }
   h->tab = h->tmin = nullptr; h->args = nullptr;
   h->J = h->S = 0;
+  h->tab_J = h->tab_S = 0;
 }
 
 static void free_search(sb_handle* h) {
@@ -190,6 +196,7 @@ int sb_destroy(sb_handle* h) {
   free_xchg(h);
   cudaFree(h->d_scratch);
   cudaFree(h->dec_buf);
+  cudaFree(h->stage_T);
   for (int i = 0; i < 2; ++i)
     if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -219,16 +226,23 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   }
   CK(cudaStreamSynchronize(h->stream));
   h->search.ready = false;  // its buffers are reused by the next sb_search_init if the shape is unchanged
-  free_table(h);
   const size_t nT = static_cast<size_t>(J) * S * G;
   const size_t ntab = static_cast<size_t>(J) * S * kSlots;
-  CK(cudaMalloc(&h->tab, ntab * sizeof(float)));
-  CK(cudaMalloc(&h->tmin, static_cast<size_t>(J) * kSlots * sizeof(float)));
-  CK(cudaMalloc(&h->args, static_cast<size_t>(J) * kSlots));
-  for (int i = 0; i < 2; ++i) {
-    CK(cudaMalloc(&h->vopt[i], static_cast<size_t>(J) * kSlots));
-    CK(cudaMalloc(&h->nvalid[i], static_cast<size_t>(J) * sizeof(int)));
+  // a re-planning loop sets a table of the same shape every interval: keep the allocations (cudaFree /
+  // cudaMalloc synchronise the device and dominate a small solve, above all with one handle per device)
+  if (h->tab == nullptr || h->tab_J != J || h->tab_S != S) {
+    free_table(h);
+    CK(cudaMalloc(&h->tab, ntab * sizeof(float)));
+    CK(cudaMalloc(&h->tmin, static_cast<size_t>(J) * kSlots * sizeof(float)));
+    CK(cudaMalloc(&h->args, static_cast<size_t>(J) * kSlots));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaMalloc(&h->vopt[i], static_cast<size_t>(J) * kSlots));
+      CK(cudaMalloc(&h->nvalid[i], static_cast<size_t>(J) * sizeof(int)));
+    }
+    h->tab_J = J;
+    h->tab_S = S;
   }
+  h->J = 0;  // not valid until the kernels below have run
   cudaPointerAttributes attr;
   const float* Tdev = T;
   float* tmp = nullptr;
@@ -237,7 +251,14 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   if (pe != cudaSuccess) cudaGetLastError();
   cudaError_t e = cudaSuccess;
   if (!on_device) {
-    e = cudaMalloc(&tmp, nT * sizeof(float));
+    if (h->stage_T_bytes < nT * sizeof(float)) {
+      cudaFree(h->stage_T);
+      h->stage_T = nullptr;
+      h->stage_T_bytes = 0;
+      e = cudaMalloc(&h->stage_T, nT * sizeof(float));
+      if (e == cudaSuccess) h->stage_T_bytes = nT * sizeof(float);
+    }
+    tmp = h->stage_T;
     if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, T, nT * sizeof(float), cudaMemcpyHostToDevice, h->stream);
     Tdev = tmp;
   }
@@ -251,7 +272,6 @@ int sb_set_table(sb_handle* h, const float* T, const uint8_t* gcount, int J, int
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h->h_args.data(), h->args, h->h_args.size(), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (tmp) cudaFree(tmp);  // released on every path, including errors
   if (e != cudaSuccess) {
     free_table(h);
     return fail(SB_ERR_CUDA, "building the table failed: %s", cudaGetErrorString(e));
@@ -1043,16 +1063,35 @@ static int search_run_impl(sb_handle** hs, int n, const sb_search_params* p, con
     for (int i = 0; i < n; ++i) wired = wired && hs[i]->xchg_ready && hs[i]->xd.world == n && hs[i]->xd.rank == i;
     if (!wired && (rc = sb_xchg_connect_local(hs, n))) return rc;
   }
-  for (int i = 0; i < n; ++i) {
+  // population set-up (allocation on first use, initialisation, first scoring, LPT seeds: several host
+  // synchronisations per device) runs on one host thread per device — done one device after the other it was
+  // 0.75 s of a 1.03 s C5 search on 8 devices (profiles/r02_c5_anneal_8dev_v1.md)
+  auto setup = [&](int i) -> int {
     sb_search_params pp = *p;
     pp.total_rounds = c->rounds;
     pp.resample_every = c->resample_every;
     pp.chain_base = p->chain_base + static_cast<uint64_t>(i) * static_cast<uint64_t>(p->chains);
     // the warm start goes to device 0 only: one copy of the previous plan is enough, the rest stays diverse
-    if ((rc = sb_search_init(hs[i], &pp, i == 0 ? warm_opt : nullptr, i == 0 ? warm_prio : nullptr))) return rc;
-    if (c->heuristic_seeds && (rc = sb_search_seed_lpt(hs[i]))) return rc;
+    int r = sb_search_init(hs[i], &pp, i == 0 ? warm_opt : nullptr, i == 0 ? warm_prio : nullptr);
+    if (r == SB_OK && c->heuristic_seeds) r = sb_search_seed_lpt(hs[i]);
+    return r;
+  };
+  if (n == 1) {
+    if ((rc = setup(0))) return rc;
+  } else {
+    std::vector<int> rcs(n, SB_OK);
+    std::vector<std::string> msgs(n);
+    std::vector<std::thread> workers;
+    for (int i = 0; i < n; ++i)
+      workers.emplace_back([&, i]() {
+        rcs[i] = setup(i);
+        if (rcs[i] != SB_OK) msgs[i] = g_err;  // the message lives in the worker's thread-local buffer
+      });
+    for (auto& w : workers) w.join();
+    for (int i = 0; i < n; ++i)
+      if (rcs[i] != SB_OK) return fail(rcs[i], "device %d: %s", hs[i]->dev.ordinal, msgs[i].c_str());
   }
-  std::vector<unsigned long long> hk(n, ~0ull);
+  std::vector<unsigned long long> hk(n, ~0ull), hres(2 * static_cast<size_t>(n), 0ull);
   std::vector<int> herr(n, 0);
   // one exchange + host read: returns the best key over all devices
   auto exchange = [&](unsigned long long* best) -> int {
@@ -1064,23 +1103,20 @@ static int search_run_impl(sb_handle** hs, int n, const sb_search_params* p, con
       *best = hk[0];
       return SB_OK;
     }
+    // per device: ONE kernel (publish the key of the saved incumbent, then fold every device's mailbox) and one
+    // 16-byte read-back of {folded key, error flag}
     for (int i = 0; i < n; ++i) {
       sb_handle* h = hs[i];
       CK(cudaSetDevice(h->dev.ordinal));
       ++h->xseq;
-      CK(xchg_post_launch(h->xd, h->search.d.keys + 1, h->xseq, h->stream));  // the key of the SAVED encoding
-    }
-    for (int i = 0; i < n; ++i) {
-      sb_handle* h = hs[i];
-      CK(cudaSetDevice(h->dev.ordinal));
-      CK(cudaMemsetAsync(h->d_scratch + 2, 0xff, sizeof(unsigned long long), h->stream));  // a timed-out fold leaves ~0
-      CK(xchg_reduce_launch(h->xd, h->xseq, h->d_scratch + 2, nullptr, h->d_xerr, h->stream));
-      CK(cudaMemcpyAsync(&hk[i], h->d_scratch + 2, sizeof(hk[i]), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaMemcpyAsync(&herr[i], h->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(xchg_post_reduce_launch(h->xd, h->search.d.keys + 1, h->xseq, h->d_scratch + 2, h->stream));
+      CK(cudaMemcpyAsync(&hres[2 * i], h->d_scratch + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     }
     for (int i = 0; i < n; ++i) {
       CK(cudaSetDevice(hs[i]->dev.ordinal));
       CK(cudaStreamSynchronize(hs[i]->stream));
+      hk[i] = hres[2 * i];
+      herr[i] = hres[2 * i + 1] != 0;
     }
     for (int i = 0; i < n; ++i) {
       if (herr[i]) return fail(SB_ERR_CUDA, "peer exchange timed out on device %d waiting for a device's key", hs[i]->dev.ordinal);

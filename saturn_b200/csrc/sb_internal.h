@@ -30,6 +30,8 @@ struct XchgPost {
 cudaError_t xchg_post_launch(const XchgDev& x, const unsigned long long* key, unsigned long long seq, cudaStream_t st);
 cudaError_t xchg_reduce_launch(const XchgDev& x, unsigned long long seq, unsigned long long* out,
                                unsigned long long* fold, int* error, cudaStream_t st);
+cudaError_t xchg_post_reduce_launch(const XchgDev& x, const unsigned long long* key, unsigned long long seq,
+                                    unsigned long long* out /*[2]: key, error*/, cudaStream_t st);
 
 struct TilePlan {
   int warps = 0;

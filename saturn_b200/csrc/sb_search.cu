@@ -62,45 +62,40 @@ __global__ void k_init_population(SearchDev s) {
 // (the Fisher-Yates swaps are dependent random accesses: ~30 clk each in shared memory instead of a
 // global-memory round trip — the serial per-thread version above cost 3.7 ms per 1 M chains,
 // profiles/r01_launch_shares.md), then the CTA writes the finished rows out with coalesced 32-bit stores
-// (padding included, so the rows need no memset).  One 64-bit RNG draw feeds two swaps (32-bit halves) or
-// four option choices (16-bit fields; at most 64 options per job, bias < 1e-3).  POS: opt bytes are emitted in
-// schedule order (opt'[i] = opt[prio[i]]), the gather happens in the write-out.
+// (padding included, so the rows need no memset).  The shuffle draws from a per-chain 64-bit LCG seeded by the
+// counter-based generator (one multiply-add per draw on the serial path instead of two 64-bit mixes); the option
+// bytes are independent of each other, so they are not staged at all: the write-out derives the four bytes of a
+// word from one counter-based draw (16-bit fields; at most 64 options per job, bias < 1e-3), for the job or —
+// POS, opt bytes in schedule order — for the jobs at those four positions.  Only the priority row lives in
+// shared memory: 24 warps per SM at J = 256.
+__device__ __forceinline__ uint8_t init_opt_byte(const SearchDev& s, uint64_t gid, int j) {
+  const uint64_t r = rng_u64(s.seed, gid, 0x100000000ull + (j >> 2));
+  const uint32_t f = static_cast<uint32_t>(r >> (16 * (j & 3))) & 0xffffu;
+  uint8_t ob = s.vopt[j * kSlots + ((f * static_cast<uint32_t>(s.nvalid[j])) >> 16)];
+  if (s.nodes > 1) {
+    const uint64_t rn = rng_u64(s.seed, gid, 0x300000000ull + (j >> 2));
+    const uint32_t fn = static_cast<uint32_t>(rn >> (16 * (j & 3))) & 0xffffu;
+    ob = static_cast<uint8_t>((ob & 7) | (((fn * static_cast<uint32_t>(s.nodes)) >> 16) << 3));
+  }
+  return ob;
+}
+
 template <int PB, bool POS>
-__global__ void k_init_population_smem(SearchDev s, int row_o, int row_p) {
+__global__ void k_init_population_smem(SearchDev s, int row_p) {
   extern __shared__ __align__(16) uint8_t sm_rows[];
   const int T = blockDim.x;
-  uint8_t* so = sm_rows + static_cast<size_t>(threadIdx.x) * row_o;
-  uint8_t* sp = sm_rows + static_cast<size_t>(T) * row_o + static_cast<size_t>(threadIdx.x) * row_p;
+  uint8_t* sp = sm_rows + static_cast<size_t>(threadIdx.x) * row_p;
   const long long c0 = static_cast<long long>(blockIdx.x) * T;
   const long long c = c0 + threadIdx.x;
   const int J = s.J;
   if (c < s.chains) {
     const uint64_t gid = s.chain_base + static_cast<uint64_t>(c);
-    for (int x = J; x < row_o; ++x) so[x] = 0;
     for (int x = J * PB; x < row_p; ++x) sp[x] = 0;
-    for (int j0 = 0; j0 < J; j0 += 4) {
-      const uint64_t r = rng_u64(s.seed, gid, 0x100000000ull + (j0 >> 2));
-      const uint64_t rn = s.nodes > 1 ? rng_u64(s.seed, gid, 0x300000000ull + (j0 >> 2)) : 0ull;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = j0 + q;
-        if (j < J) {
-          const uint32_t f = static_cast<uint32_t>(r >> (16 * q)) & 0xffffu;
-          uint8_t ob = s.vopt[j * kSlots + ((f * static_cast<uint32_t>(s.nvalid[j])) >> 16)];
-          if (s.nodes > 1) {
-            const uint32_t fn = static_cast<uint32_t>(rn >> (16 * q)) & 0xffffu;
-            ob = static_cast<uint8_t>((ob & 7) | (((fn * static_cast<uint32_t>(s.nodes)) >> 16) << 3));
-          }
-          so[j] = ob;
-        }
-      }
-    }
     for (int j = 0; j < J; ++j) prio_st<PB>(sp, j, j);
-    uint64_t r = 0;
+    uint64_t x = rng_u64(s.seed, gid, 0x200000000ull) | 1ull;
     for (int i = J - 1; i > 0; --i) {
-      // draws are consumed from the top index down: the odd index of a pair fetches the 64-bit word
-      if ((i & 1) || i == J - 1) r = rng_u64(s.seed, gid, 0x200000000ull + (i >> 1));
-      const uint32_t u = (i & 1) ? static_cast<uint32_t>(r >> 32) : static_cast<uint32_t>(r);
+      x = x * 6364136223846793005ull + 1442695040888963407ull;
+      const uint32_t u = static_cast<uint32_t>((x ^ (x >> 29)) >> 32);
       const int k = static_cast<int>((static_cast<uint64_t>(u) * static_cast<uint32_t>(i + 1)) >> 32);
       const int a = prio_ld<PB>(sp, i), b = prio_ld<PB>(sp, k);
       prio_st<PB>(sp, i, b);
@@ -110,20 +105,16 @@ __global__ void k_init_population_smem(SearchDev s, int row_o, int row_p) {
   __syncthreads();
   const int wo = static_cast<int>(s.stride_o >> 2), wp = static_cast<int>(s.stride_p >> 2);  // strides are multiples of 32 B
   for (int r = 0; r < T && c0 + r < s.chains; ++r) {
-    const uint8_t* ro = sm_rows + static_cast<size_t>(r) * row_o;
-    const uint8_t* rp = sm_rows + static_cast<size_t>(T) * row_o + static_cast<size_t>(r) * row_p;
+    const uint8_t* rp = sm_rows + static_cast<size_t>(r) * row_p;
+    const uint64_t gid = s.chain_base + static_cast<uint64_t>(c0 + r);
     uint32_t* go = reinterpret_cast<uint32_t*>(s.cur_o + (c0 + r) * s.stride_o);
     uint32_t* gp = reinterpret_cast<uint32_t*>(s.cur_p + (c0 + r) * s.stride_p);
     for (int w = threadIdx.x; w < wo; w += T) {
       uint32_t v = 0;
-      if (!POS) {
-        if (w * 4 < row_o) v = reinterpret_cast<const uint32_t*>(ro)[w];
-      } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = w * 4 + q;
-          if (i < J) v |= static_cast<uint32_t>(ro[prio_ld<PB>(rp, i)]) << (8 * q);
-        }
+      for (int q = 0; q < 4; ++q) {
+        const int i = w * 4 + q;
+        if (i < J) v |= static_cast<uint32_t>(init_opt_byte(s, gid, POS ? prio_ld<PB>(rp, i) : i)) << (8 * q);
       }
       go[w] = v;
     }
@@ -607,19 +598,19 @@ static int init_row(int bytes) {
 // then zero-fills the rows and runs the per-thread global-memory kernel.
 template <bool POS>
 static cudaError_t init_population_smem(const SearchDev& s, cudaStream_t st) {
-  const int row_o = init_row(s.J), row_p = init_row(s.J * s.pb);
+  const int row_p = init_row(s.J * s.pb);
   int threads = 128;
-  while (threads >= 32 && static_cast<size_t>(threads) * (row_o + row_p) > 100 * 1024) threads >>= 1;
+  while (threads >= 32 && static_cast<size_t>(threads) * row_p > 48 * 1024) threads >>= 1;
   if (threads < 32) {
     threads = 32;
-    if (static_cast<size_t>(threads) * (row_o + row_p) > 220 * 1024) return cudaErrorNotSupported;
+    if (static_cast<size_t>(threads) * row_p > 220 * 1024) return cudaErrorNotSupported;
   }
-  const size_t smem = static_cast<size_t>(threads) * (row_o + row_p);
+  const size_t smem = static_cast<size_t>(threads) * row_p;
   const int grid = static_cast<int>((s.chains + threads - 1) / threads);
   auto launch = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kern<<<grid, threads, smem, st>>>(s, row_o, row_p);
+    kern<<<grid, threads, smem, st>>>(s, row_p);
     return cudaGetLastError();
   };
   return s.pb == 1 ? launch(k_init_population_smem<1, POS>) : launch(k_init_population_smem<2, POS>);

@@ -78,6 +78,50 @@ __global__ void k_xchg_reduce(XchgDev x, unsigned long long seq, unsigned long l
   }
 }
 
+// post + fold in one launch (the in-process multi-device search, sb_api.cu): thread 0 publishes this device's
+// key, then lane r waits for device r's mailbox to show round `seq`; out[0] = MIN over all devices (~0 on a
+// timed-out wait), out[1] = 1 if a wait timed out.
+__global__ void k_xchg_post_reduce(XchgDev x, const unsigned long long* key, unsigned long long seq,
+                                   unsigned long long* out) {
+  const int r = threadIdx.x;
+  if (r == 0) {
+    unsigned long long* slot = x.local + (seq & 1ull) * 2;
+    st_relaxed_sys(slot, *key);
+    st_release_sys(slot + 1, seq);
+  }
+  __syncwarp();
+  unsigned long long k = ~0ull;
+  bool ok = true;
+  if (r < x.world) {
+    const unsigned long long* slot = x.peer[r] + (seq & 1ull) * 2;
+    unsigned spins = 0;
+    while (ld_acquire_sys(slot + 1) < seq) {
+      if (++spins > (1u << 22)) {
+        ok = false;
+        break;
+      }
+      __nanosleep(64);
+    }
+    if (ok) k = ld_relaxed_sys(slot);
+  }
+  const unsigned all_ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, d);
+    k = o < k ? o : k;
+  }
+  if (threadIdx.x == 0) {
+    out[0] = all_ok ? k : ~0ull;
+    out[1] = all_ok ? 0ull : 1ull;
+  }
+}
+
+cudaError_t xchg_post_reduce_launch(const XchgDev& x, const unsigned long long* key, unsigned long long seq,
+                                    unsigned long long* out, cudaStream_t st) {
+  k_xchg_post_reduce<<<1, 32, 0, st>>>(x, key, seq, out);
+  return cudaGetLastError();
+}
+
 cudaError_t xchg_post_launch(const XchgDev& x, const unsigned long long* key, unsigned long long seq, cudaStream_t st) {
   k_xchg_post<<<1, 32, 0, st>>>(x, key, seq);
   return cudaGetLastError();

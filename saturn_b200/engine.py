@@ -382,14 +382,21 @@ class MultiEngine:
         self._lib = self.engines[0]._lib
         self.device = self.engines[0].device
         self.devices = devices
+        self._pool = None
 
     def close(self):
+        if self._pool is not None:
+            self._pool.shutdown()
+            self._pool = None
         for e in self.engines:
             e.close()
 
     def set_table(self, T, gcount=None, sentinel=None, nodes: int = 1):
-        for e in self.engines:
-            e.set_table(T, gcount, sentinel=sentinel, nodes=nodes)
+        # one host thread per device: sb_set_table synchronises its stream (ctypes releases the GIL in the call)
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(self.engines))
+        list(self._pool.map(lambda e: e.set_table(T, gcount, sentinel=sentinel, nodes=nodes), self.engines))
         return self
 
     J = property(lambda self: self.engines[0].J)
