@@ -542,6 +542,24 @@ def main():
                              "encoding": ("opt by schedule position, min-over-strategies table (the population "
                                           "encoding of the J > 512 search)" if by_pos else "job-indexed opt, full table")}
             del oc, pc, outc
+        # the kernel shape the north star sketches (slot times across lanes + warp shuffles), same C4 candidates
+        eng.set_table(T)
+        Ba = 4 * WAVE
+        for _ in range(2):
+            eng.eval(opt[:Ba], prio[:Ba], integer_starts=ints, out=out[:Ba], alt_shape=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(8):
+            eng.eval(opt[:Ba], prio[:Ba], integer_starts=ints, out=out[:Ba], alt_shape=True)
+        c1.record()
+        torch.cuda.synchronize()
+        msa = c0.elapsed_time(c1) / 8
+        configs["C4_alt_shape"] = {"J": J, "S": S, "candidates_per_launch": Ba, "ms_per_launch": msa,
+                                   "candidates_per_s": Ba / (msa * 1e-3), "eval_path": eng.last_eval_path(),
+                                   "frac": Ba * bytes_per_candidate(J) / (msa * 1e-3) / 1e9 / peak_c,
+                                   "encoding": "SB_FLAG_ALT_WARPSCAN: 8 lanes per candidate, 4 candidates per warp, the "
+                                               "sorted slot times shifted with shuffles — measured for comparison with "
+                                               "the shipped lane-per-candidate kernel (`value`), not used"}
         eng.set_table(T)
 
     if rank == 0:

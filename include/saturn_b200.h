@@ -85,6 +85,11 @@ typedef enum sb_status {
 #define SB_FLAG_FOLD_PREV 16u     /* with SB_FLAG_POST_KEY: the kernel's prologue first MINs into *best_key the keys
                                      all ranks published in the PREVIOUS round (one-round pipelined exchange:
                                      the NVLink latency hides under the evaluation); finish with sb_xchg_reduce */
+#define SB_FLAG_ALT_WARPSCAN 32u   /* sb_eval only, one node: score with the ALTERNATE kernel shape — a candidate's 8
+                                     slot times spread over 8 lanes and combined with warp shuffles (the shape
+                                     BASELINE.json's north_star sketches), 4 candidates per warp.  Same results;
+                                     kept to be measured against the shipped lane-per-candidate kernel
+                                     (profiles/r02_alt_shape.md), not to be used. */
 #define SB_IPC_HANDLE_BYTES 64
 
 typedef struct sb_handle sb_handle;
@@ -127,6 +132,7 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
             unsigned flags, float* makespan_out, uint64_t* best_key, uint32_t id_base);
 
 /* which kernel the last sb_eval / sb_eval_host on this handle used:
+ * 6 = the alternate warp-shuffle kernel (SB_FLAG_ALT_WARPSCAN),
  * 5 = position-major kernel (SB_FLAG_OPT_BY_POSITION): both rows streamed with 256-bit loads,
  * 4 = as 3 but with the runtime table read from global memory (it does not fit in shared memory),
  * 3 = tile kernel, opt rows by TMA bulk copy + prio rows streamed with 256-bit loads (rows 32-byte

@@ -348,6 +348,18 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
     h->last_path = 5;
     return SB_OK;
   }
+  if (flags & SB_FLAG_ALT_WARPSCAN) {
+    if (flags & (SB_FLAG_POST_KEY | SB_FLAG_FOLD_PREV))
+      return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_ALT_WARPSCAN cannot be combined with the fused key exchange");
+    cudaError_t e = eval_alt_launch(h->dev, c, h->stream);
+    if (e == cudaErrorNotSupported) {
+      cudaGetLastError();
+      return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_ALT_WARPSCAN needs one node and a table that fits in shared memory");
+    }
+    CK(e);
+    h->last_path = 6;
+    return SB_OK;
+  }
   c.force_generic = (flags & 0x80000000u) ? 1 : 0;  // test hooks: 0x80000000 generic kernel, 0x40000000 no streaming
   const bool post = (flags & SB_FLAG_POST_KEY) != 0;
   if (post) {

@@ -97,6 +97,7 @@ struct SearchFuse {
 
 int plan_tiles(const Device& dev, int J, int SG, int pb, bool stream, int nodes, TilePlan* tp, bool tab_global = false);
 cudaError_t eval_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path_used);
+cudaError_t eval_alt_launch(const Device& dev, const EvalCall& c, cudaStream_t st);  // sb_eval_alt.cu
 int search_round_mode(const Device& dev, int J, int SG, int nodes);
 cudaError_t search_round_launch(const Device& dev, const EvalCall& c, const SearchFuse& sf, cudaStream_t st);
 cudaError_t eval_full_launch(const Device& dev, const EvalCall& c, float* start, uint32_t* slotmask, cudaStream_t st);

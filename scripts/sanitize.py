@@ -17,16 +17,24 @@ for (J, S, G, B) in [(64, 6, 8, 2000), (100, 3, 8, 777), (300, 2, 8, 500)]:
     c = eng.eval(opt.contiguous(), prio.contiguous())
     d = eng.eval(opt, prio, _force_generic=True)
     e, st, mk = eng.eval_full(opt, prio)
+    f = eng.eval(opt, prio, alt_shape=True)                  # round 2: the warp-shuffle shape
+    g = eng.eval(opt, prio, _plain_addr=True)
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d) and torch.equal(a, e)
+    assert torch.equal(a, f) and torch.equal(a, g)
     assert eng.validate(opt, prio) == 0
     r = run_search(eng, chains=2048, rounds=6, use_dist=False)
     eng.decode(r.opt, r.prio)
+    # round 2: incremental rounds with the verify hook (snapshots, windowed moves, in-kernel tournament)
+    r = run_search(eng, chains=2048, rounds=20, reduced=True, use_dist=False, _extra_flags=0x08000000)
+    assert eng.search_verify_count() == 0 and eng.search_validate() == 0
 # large J: position-major search populations (k_search_pos), ragged tails, one and two nodes
 for (J, nodes, chains) in [(1030, 1, 300), (777, 2, 130), (513, 1, 64)]:
     T, valid = synth_table(J, 1, 8, seed=3)
     eng.set_table(T, nodes=nodes)
     r = run_search(eng, chains=chains, rounds=6, reduced=True, use_dist=False)
+    r = run_search(eng, chains=chains, rounds=18, reduced=True, use_dist=False, _extra_flags=0x08000000, resample_every=4)
+    assert eng.search_verify_count() == 0 and eng.search_validate() == 0
     eng.search_inject(r.opt, r.prio, copies=3)
     eng.search_resample()
     eng.search_round(2)

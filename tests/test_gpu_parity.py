@@ -72,6 +72,13 @@ def test_all_kernel_paths_agree(engine):
         x = engine.eval(opt, prio, integer_starts=ints)
         y = engine.eval(opt, prio, integer_starts=ints, _plain_addr=True)
         assert engine.last_eval_path() == 3 and torch.equal(x, y)
+    for ints in (True, False):            # the alternate warp-shuffle shape (4 candidates per warp, 8 lanes each)
+        x = engine.eval(opt, prio, integer_starts=ints)
+        key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=engine.device)
+        y = engine.eval(opt, prio, integer_starts=ints, alt_shape=True, best_key=key, id_base=7)
+        assert engine.last_eval_path() == 6 and torch.equal(x, y)
+        k = int(key.item())
+        assert (k & 0xffffffff) == 7 + int(torch.argmin(x).item()) and (k >> 32) == int(x.min().view(torch.int32).item())
     opt_u = opt.contiguous()              # row stride J = 100 bytes: not 16-byte aligned
     prio_u = prio.contiguous()
     b = engine.eval(opt_u, prio_u)
@@ -94,6 +101,7 @@ def test_u16_priorities(engine, J, S):
     g = engine.eval(opt, prio, _force_generic=True)
     assert torch.equal(mk, g)
     assert torch.equal(mk, engine.eval(opt, prio, _no_stream=True))
+    assert torch.equal(mk, engine.eval(opt, prio, alt_shape=True)) and engine.last_eval_path() == 6
 
 
 def test_reduced_table_matches_profiler_reduction(engine):
@@ -427,3 +435,27 @@ def test_opt_by_position_is_refused_where_it_cannot_run(engine):
     o2, p2 = random_candidates(engine, 32, valid2, seed=1)
     with pytest.raises(RuntimeError, match="shared memory"):
         engine.eval(opt_by_position(o2, p2), p2, by_position=True)
+
+
+def test_c5_route_parity(engine):
+    """The route bench.py's `configs.C5` measures and the J > 512 search uses: the FULL C5 table (J = 1024,
+    S = 8: 256 KB, does not fit in shared memory) is reduced over strategies on the device, candidates carry
+    (k - 1) per schedule position, kernel path 5 scores them on the 32 KB reduced table — bit-exact against the
+    oracle run on the host-side reduction of the same table, integer and real-valued starts."""
+    from saturn_b200.engine import opt_by_position
+    from saturn_b200.synth import synth_table
+    J, S, G, B = 1024, 8, 8, 1200
+    T, valid = synth_table(J, S, G, seed=0)
+    engine.set_table(T)
+    vr = valid.any(axis=1, keepdims=True)
+    opt, prio = random_candidates(engine, B, vr, seed=9)
+    tab = R.canon_table(T, range(1, G + 1))
+    tmin, args = R.reduce_table(tab)
+    dev_tmin, dev_args = engine.reduced_table()
+    assert np.array_equal(dev_tmin, tmin) and np.array_equal(dev_args[np.isfinite(tmin)], args[np.isfinite(tmin)])
+    for ints in (True, False):
+        ref = c_oracle.evaluate(tmin[:, None, :], opt.cpu().numpy(), prio.cpu().numpy(), ints, np.float32, threads=8)
+        got = engine.eval(opt_by_position(opt, prio), prio, integer_starts=ints, reduced=True, by_position=True)
+        assert engine.last_eval_path() == 5
+        assert np.array_equal(got.cpu().numpy(), ref)
+        assert torch.equal(got, engine.eval(opt, prio, integer_starts=ints, reduced=True))   # job-indexed tile kernel
