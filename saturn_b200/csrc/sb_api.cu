@@ -1117,16 +1117,21 @@ static int search_run_impl(sb_handle** hs, int n, const sb_search_params* p, con
     }
     // per device: ONE kernel (publish the key of the saved incumbent, then fold every device's mailbox) and one
     // 16-byte read-back of {folded key, error flag}
+    // Every device's kernel must be QUEUED before the host waits on any of them: a kernel spins until all
+    // devices have published, and a device-to-host copy into pageable memory blocks the host until the stream
+    // has drained (copy right behind the launch = device 0 waits for a kernel that was never launched:
+    // the first version of this loop timed out exactly so).
     for (int i = 0; i < n; ++i) {
       sb_handle* h = hs[i];
       CK(cudaSetDevice(h->dev.ordinal));
       ++h->xseq;
       CK(xchg_post_reduce_launch(h->xd, h->search.d.keys + 1, h->xseq, h->d_scratch + 2, h->stream));
-      CK(cudaMemcpyAsync(&hres[2 * i], h->d_scratch + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     }
     for (int i = 0; i < n; ++i) {
-      CK(cudaSetDevice(hs[i]->dev.ordinal));
-      CK(cudaStreamSynchronize(hs[i]->stream));
+      sb_handle* h = hs[i];
+      CK(cudaSetDevice(h->dev.ordinal));
+      CK(cudaMemcpyAsync(&hres[2 * i], h->d_scratch + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
       hk[i] = hres[2 * i];
       herr[i] = hres[2 * i + 1] != 0;
     }

@@ -1,0 +1,31 @@
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l)
+timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 | tee gpurun_out/r02_pytest_multi_${N}gpu_v2.log
+timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/r02_solve_devices_${N}.md
+# saturn.solver.solve(task_list, devices=n) on the C4 task set: wall time and candidates/s vs the number of devices
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+from saturn_b200 import Strategy, solve
+from saturn_b200 import solver as S
+from saturn_b200.synth import synth_table
+class T_:
+    def __init__(self, n, s): self.name, self.strategies, self.selected_strategy = n, s, None
+    def select_strategy(self, s): self.selected_strategy = s
+T, valid = synth_table(256, 8, 8, seed=0)
+tmin = np.where(valid, T, np.inf).min(axis=1)
+tasks = [T_("t%d" % j, {g + 1: Strategy("x", g + 1, {}, float(tmin[j, g])) for g in range(8) if np.isfinite(tmin[j, g])}) for j in range(256)]
+print("| devices | rounds | wall ms (median of 5) | candidates | candidates / s | makespan | speed-up |\n|---|---|---|---|---|---|---|")
+base = {}
+for rounds in (200, 800):
+    for n in [d for d in (1, 2, 4, 8) if d <= torch.cuda.device_count()]:
+        solve(tasks, None, devices=n, rounds=16)
+        ws = []
+        for _ in range(5):
+            t0 = time.perf_counter(); out = solve(tasks, None, devices=n, rounds=rounds); ws.append(time.perf_counter() - t0)
+        w = float(np.median(ws)); c = S.last_stats["candidates"]
+        base.setdefault(rounds, c / w)
+        print("| %d | %d | %.2f | %.3e | %.3e | %.1f | %.2fx |" % (n, rounds, w * 1e3, c, c / w, out[5], (c / w) / base[rounds]), flush=True)
+PY
+timeout 300 python scripts/anneal.py --config C5 --chains 131072 --candidates $((N*125000000)) --devices $N > gpurun_out/r02_c5_anneal_${N}dev.md 2> gpurun_out/r02_c5_anneal_${N}dev.err; tail -3 gpurun_out/r02_c5_anneal_${N}dev.err; head -8 gpurun_out/r02_c5_anneal_${N}dev.md; tail -3 gpurun_out/r02_c5_anneal_${N}dev.md
+timeout 300 python scripts/anneal.py --config C4 --chains 227328 --candidates $((N*500000000)) --devices $N > gpurun_out/r02_c4_anneal_${N}dev.md 2> gpurun_out/r02_c4_anneal_${N}dev.err; head -6 gpurun_out/r02_c4_anneal_${N}dev.md; tail -3 gpurun_out/r02_c4_anneal_${N}dev.md
