@@ -388,7 +388,9 @@ __device__ __forceinline__ PosMove make_pos_move_win(const SearchFuse& sf, int r
   return m;
 }
 
-template <int PB, bool INT, bool MULTI>
+// EVAL: the scoring-only instantiation (sb_eval with SB_FLAG_OPT_BY_POSITION, population scoring after
+// initialisation / injection): the move, snapshot and acceptance code folds away at compile time.
+template <int PB, bool INT, bool MULTI, bool EVAL = false>
 __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
@@ -508,19 +510,19 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     // bound when the unrolled 32-step body is inlined several times): the scoring pass of eval_only, the
     // unmodified pass that fills the snapshots (r = -1), the rounds and the verify hook's recomputation all go
     // through it.
-    float cm = (active && !a.eval_only) ? a.sf.cur_mk[c] : 0.f;
-    bool moving = active && !a.eval_only;  // false from the round in which this lane lowers the global best key
+    float cm = (active && !EVAL) ? a.sf.cur_mk[c] : 0.f;
+    bool moving = active && !EVAL;  // false from the round in which this lane lowers the global best key
     const uint64_t gid = a.sf.chain_base + static_cast<uint64_t>(c);
     // incremental rounds (one node): windows of wblk 32-position blocks, at most 32 of them
     const int nout_all = (J + 31) / 32;
     const int wblk = (nout_all + 31) / 32;
     const int nwin = (nout_all + wblk - 1) / wblk;
-    const bool win = !a.eval_only && !MULTI && a.sf.win != 0 && nwin >= 2;
+    const bool win = !EVAL && !MULTI && a.sf.win != 0 && nwin >= 2;
     const bool inc = win && a.sf.snap != nullptr;
     float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
     uint32_t par = 0;
-    const uint32_t inc_bits = a.eval_only ? 0u : launch_incumbent_bits(a.sf);
-    const int r_end = a.eval_only ? 1 : a.sf.nrounds;
+    const uint32_t inc_bits = EVAL ? 0u : launch_incumbent_bits(a.sf);
+    const int r_end = EVAL ? 1 : a.sf.nrounds;
 #pragma unroll 1
     for (int r = inc ? -1 : 0; r < r_end; ++r) {
       const int round = a.sf.round + r;
@@ -549,7 +551,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
         else if (active && __float_as_uint(got) != __float_as_uint(mk)) atomicAdd(a.sf.verify_bad, 1ull);
       }
       if (fill) continue;
-      if (a.eval_only) {
+      if (EVAL) {
         if (active) a.sf.cur_mk[c] = mk;
       } else if (moving) {
         bool acc = mk <= cm;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
         }
       }
       if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
-      if (active && !a.eval_only && __float_as_uint(mk) < inc_bits) moving = false;  // see launch_incumbent_bits
+      if (active && !EVAL && __float_as_uint(mk) < inc_bits) moving = false;  // see launch_incumbent_bits
     }
   }
   if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
@@ -713,6 +715,14 @@ cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float
     kern<<<grid, warps * 32, smem, st>>>(a);
     return cudaGetLastError();
   };
+  if (eval_only) {
+    if (s.pb == 1) {
+      if (multi) return ints ? launch(k_search_pos<1, true, true, true>) : launch(k_search_pos<1, false, true, true>);
+      return ints ? launch(k_search_pos<1, true, false, true>) : launch(k_search_pos<1, false, false, true>);
+    }
+    if (multi) return ints ? launch(k_search_pos<2, true, true, true>) : launch(k_search_pos<2, false, true, true>);
+    return ints ? launch(k_search_pos<2, true, false, true>) : launch(k_search_pos<2, false, false, true>);
+  }
   if (s.pb == 1) {
     if (multi) return ints ? launch(k_search_pos<1, true, true>) : launch(k_search_pos<1, false, true>);
     return ints ? launch(k_search_pos<1, true, false>) : launch(k_search_pos<1, false, false>);

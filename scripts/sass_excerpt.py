@@ -77,7 +77,8 @@ def main():
     want = [("_ZN2sb12k_eval_tilesILi1ELb1ELb1ELb0ELb0ELb0ELi1EEEvNS_8TileArgsE", "the measured kernel (bench `value`): C4, integer starts, prio streamed, look-up addresses on the FMA pipe", 32),
             ("_ZN2sb12k_eval_tilesILi1ELb1ELb1ELb0ELb0ELb0ELi0EEEvNS_8TileArgsE", "the same kernel with plain C++ addressing (test hook 0x02000000; the round-1 form)", 32),
             ("_ZN2sb12k_eval_tilesILi1ELb1ELb0ELb0ELb1ELb0ELi0EEEvNS_8TileArgsE", "fused search round (solve()): rows in shared memory, incremental scoring", 16),
-            ("_ZN2sb12k_search_posILi2ELb1ELb0EEEvNS_7PosArgsE", "position-major search round (J > ~450, u16 priorities)", 32)]
+            ("_ZN2sb12k_search_posILi2ELb1ELb0ELb0EEEvNS_7PosArgsE", "position-major search round (J > ~450, u16 priorities)", 32),
+            ("_ZN2sb13k_eval_groupsILi1ELb1EEEvNS_7AltArgsE", "the alternate shape (SB_FLAG_ALT_WARPSCAN): 8 lanes per candidate, shuffles; the block is the 8 steps of one look-up batch for 4 candidates", 8)]
     for name, what, steps in want:
         if name not in fns:
             print("## %s\n\nnot found in this build\n" % name)
