@@ -240,6 +240,9 @@ def main():
     ap.add_argument("--config", default="C4", choices=["C2", "C3", "C4", "C5"],
                     help="BASELINE config shape (C4 is the headline; the others are diagnostic runs)")
     ap.add_argument("--reduced", action="store_true", help="evaluate on the min-over-strategies table")
+    ap.add_argument("--solve-devices", type=int, default=0,
+                    help="N = 1 only, opt-in: also time saturn.solver.solve(..., devices=D) — ONE process driving D GPUs "
+                         "(it touches GPUs beyond --gpus, so it is never run by default)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200:
@@ -466,7 +469,7 @@ def main():
                      "makespan": plan[5], "h2d_bytes": int(J * 8 * 4), "d2h_bytes": int(J * (8 + 4 + 1 + 1 + 1)),
                      "api": "saturn.solver.solve(task_list) -> (sta, tga, bss, bna, boa, makespan); per rank"}
         # one process, every GPU of the node: saturn.solver.solve(..., devices=N) (sb_search_run_multi)
-        ndev = torch.cuda.device_count()
+        ndev = min(args.solve_devices, torch.cuda.device_count())
         if world == 1 and ndev > 1:
             solve(c4_tasks, None, devices=ndev, rounds=8)
             t0 = time.perf_counter()

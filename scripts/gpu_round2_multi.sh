@@ -5,7 +5,7 @@ timeout 900 python -m pytest tests/test_gpu_multi.py -q -v 2>&1 | tail -25 | tee
 for n in 1 2 4 8; do
   if [ $n -le $N ]; then
     if [ $n -eq 1 ]; then
-      timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_of${N}.log 2> gpurun_out/r02_bench_n1_of${N}.err
+      timeout 900 python bench.py --steps 20 --warmup 5 --solve-devices $N > gpurun_out/r02_bench_n1_of${N}.log 2> gpurun_out/r02_bench_n1_of${N}.err
     else
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02_bench_n${n}_of${N}.log 2> gpurun_out/r02_bench_n${n}_of${N}.err
     fi
