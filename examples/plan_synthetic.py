@@ -1,6 +1,6 @@
 """Plan a synthetic multi-model workload with the B200 solver through Saturn's own API.
 
-    python examples/plan_synthetic.py [--jobs 32] [--nodes 1]
+    python examples/plan_synthetic.py [--jobs 32] [--nodes 1] [--devices 1] [--dense]
 
 Stands in for the reference's examples/wikitext103/WikiText103.py after the trial runner has
 filled `task.strategies` (saturn/trial_runner/PerformanceEvaluator.py:96-115): here the runtimes are
@@ -22,6 +22,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=32)
     ap.add_argument("--nodes", type=int, default=1)
+    ap.add_argument("--devices", type=int, default=1, help="GPUs of this process the search is sharded over")
+    ap.add_argument("--dense", action="store_true", help="also plan from the dense T[J][S][G] tensor (solve_table)")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
     save_dir = tempfile.mkdtemp(prefix="saturn_b200_")
@@ -40,7 +42,7 @@ def main():
         tasks.append(t)
 
     # --- Saturn API -------------------------------------------------------------------------
-    sta, tga, bss, bna, boa, makespan = solve(tasks, nodes=args.nodes)
+    sta, tga, bss, bna, boa, makespan = solve(tasks, nodes=args.nodes, devices=args.devices)
     node_per_task, deps, starts = convert_into_comprehensible(tasks, bss, boa, tga, bna, sta)
 
     print("planned %d tasks on %d node(s): makespan %.0f s" % (len(tasks), args.nodes, makespan))
@@ -49,6 +51,21 @@ def main():
         print("  %-9s node %d  start %8.0f  %d GPU(s)  %-8s  %8.0f s  after %s" % (
             t.name, node_per_task[t], s, st.gpu_apportionment, st.executor, st.runtime,
             [d.name for d in deps[t]][:3] if t in deps else []))
+
+    if args.dense:
+        # the same plan from the un-reduced profiler tensor: what the trial runner measured, before it is
+        # collapsed into task.strategies (saturn_b200.solver.table_from_trials / solve_table)
+        from saturn_b200 import solve_table
+        execs = ["spilled", "fsdp", "pipeline"]
+        T = np.full((len(tasks), len(execs), 8), 1e6, dtype=np.float32)
+        mask = np.zeros(T.shape, dtype=bool)
+        for j, t in enumerate(tasks):
+            for g, st in t.strategies.items():
+                if st.executor is not None:
+                    T[j, execs.index(st.executor), g - 1] = st.runtime
+                    mask[j, execs.index(st.executor), g - 1] = True
+        out = solve_table(T, mask, nodes=args.nodes, devices=args.devices)
+        print("dense entry: makespan %.0f s; executor per task %s ..." % (out[5], [execs[i] for i in out[6][:6]]))
 
 
 if __name__ == "__main__":

@@ -841,6 +841,7 @@ static SearchFuse make_fuse(const SearchState& s, int round, int n) {
   sf.resample_every = s.p.resample_every > 0 ? s.p.resample_every : 0;
   sf.deal = static_cast<int>(s.launches & 1);
   sf.win = s.win ? 1 : 0;
+  sf.win_bias = (s.p.flags & 0x01000000u) ? 1 : 0;
   sf.snap = s.inc ? s.snap : nullptr;
   sf.verify_bad = s.verify ? s.verify_bad : nullptr;
   sf.keep.counter = s.tail_counter;

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
         if (win && !fill) {
           const uint64_t wr = rng_u64(a.sf.seed ^ 0x31d0ull, a.sf.chain_base + static_cast<uint64_t>(a.sf.deal ? tile : b0),
                                       static_cast<uint64_t>(round));
-          w0 = static_cast<int>(bounded32(wr, nwin));
+          w0 = draw_window(wr, nwin, a.sf.win_bias);
         }
         Move mv;
         mv.kind = 0; mv.a = mv.b = mv.va = mv.vb = 0;

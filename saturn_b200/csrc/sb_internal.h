@@ -83,6 +83,7 @@ struct SearchFuse {
   // the other buffer; accepting the move flips which buffer is current (a per-lane bit per boundary), so a
   // rejected move costs nothing to undo.  An unmodified pass at the start of the launch fills the buffers.
   int win = 0;                    // 1: moves are drawn inside a per-warp window (also without snapshots)
+  int win_bias = 0;               // 0: windows uniform; 1: P(w) ~ w + 1 (draw_window)
   float* snap = nullptr;          // scratch, (ntiles * nbound * 2 * 9 * 32) floats; nullptr = score every proposal from position 0
   unsigned long long* verify_bad = nullptr;  // test hook: also score from position 0 and count differing results here
   // keep-best in the kernel's tail (KeepBest::counter != nullptr): the CTA that finishes last copies the

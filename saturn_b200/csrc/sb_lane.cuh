@@ -262,6 +262,21 @@ __device__ __forceinline__ Move apply_move(const SearchFuse& sf, int round, int 
   return m;
 }
 
+// The window of a round, from one 64-bit draw shared by the warp.  bias 0: uniform over the nwin windows.
+// bias 1 (experiment, sb_search_params.flags 0x01000000): P(w) proportional to w + 1 — later windows skip more
+// of the schedule (mean resume point 0.58 instead of 0.44 of the way in at 8 windows) at the price of fewer
+// moves near the front of the schedule.
+__device__ __forceinline__ int draw_window(uint64_t r, int nwin, int bias) {
+  if (bias == 0) return static_cast<int>(bounded32(r, nwin));
+  // triangular: pick t uniform in [0, nwin (nwin + 1) / 2) and invert the cumulative sum
+  const uint32_t tot = static_cast<uint32_t>(nwin) * (nwin + 1) / 2;
+  const uint32_t t = bounded32(r, tot);
+  int w = static_cast<int>((sqrtf(8.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
+  while (static_cast<uint32_t>(w + 1) * (w + 2) / 2 <= t) ++w;   // fix the float rounding
+  while (static_cast<uint32_t>(w) * (w + 1) / 2 > t) --w;
+  return w;
+}
+
 // Windowed form of apply_move (incremental rounds, see SearchFuse::snap): the first schedule position a move
 // changes lies inside [w0, w0 + wlen), positions before w0 are untouched.  Same move kinds and mix; a job is
 // addressed through its position (the option of the job scheduled i-th changes), a swap pairs a position of the

@@ -62,41 +62,42 @@ __global__ void k_init_population(SearchDev s) {
 // (the Fisher-Yates swaps are dependent random accesses: ~30 clk each in shared memory instead of a
 // global-memory round trip — the serial per-thread version above cost 3.7 ms per 1 M chains,
 // profiles/r01_launch_shares.md), then the CTA writes the finished rows out with coalesced 32-bit stores
-// (padding included, so the rows need no memset).  The shuffle draws from a per-chain 64-bit LCG seeded by the
-// counter-based generator (one multiply-add per draw on the serial path instead of two 64-bit mixes); the option
+// (padding included, so the rows need no memset).  The shuffle draws from a per-chain 32-bit LCG seeded by the
+// counter-based generator (one IMAD per draw on the serial path instead of two 64-bit mixes); the option
 // bytes are independent of each other, so they are not staged at all: the write-out derives the four bytes of a
-// word from one counter-based draw (16-bit fields; at most 64 options per job, bias < 1e-3), for the job or —
-// POS, opt bytes in schedule order — for the jobs at those four positions.  Only the priority row lives in
-// shared memory: 24 warps per SM at J = 256.
-__device__ __forceinline__ uint8_t init_opt_byte(const SearchDev& s, uint64_t gid, int j) {
-  const uint64_t r = rng_u64(s.seed, gid, 0x100000000ull + (j >> 2));
-  const uint32_t f = static_cast<uint32_t>(r >> (16 * (j & 3))) & 0xffffu;
-  uint8_t ob = s.vopt[j * kSlots + ((f * static_cast<uint32_t>(s.nvalid[j])) >> 16)];
-  if (s.nodes > 1) {
-    const uint64_t rn = rng_u64(s.seed, gid, 0x300000000ull + (j >> 2));
-    const uint32_t fn = static_cast<uint32_t>(rn >> (16 * (j & 3))) & 0xffffu;
-    ob = static_cast<uint8_t>((ob & 7) | (((fn * static_cast<uint32_t>(s.nodes)) >> 16) << 3));
-  }
-  return ob;
+// word from two 32-bit hashes of (chain id, word) (16 random bits per byte; at most 64 options per job, bias
+// < 1e-3), for the job or — POS, opt bytes in schedule order — for the jobs at those four positions, with the
+// (row, word) pairs of the CTA dealt over all threads and the option lists staged in shared memory.  Only the
+// priority rows and those lists live in shared memory: 24 warps per SM at J = 256.
+// 32-bit avalanche (murmur3 finaliser): the option choices of a word need 4 x 16 random bits per (chain, word)
+__device__ __forceinline__ uint32_t hash32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
 }
 
 template <int PB, bool POS>
 __global__ void k_init_population_smem(SearchDev s, int row_p) {
   extern __shared__ __align__(16) uint8_t sm_rows[];
   const int T = blockDim.x;
+  const int J = s.J;
   uint8_t* sp = sm_rows + static_cast<size_t>(threadIdx.x) * row_p;
+  // the proposable-option lists of all jobs, staged once per CTA: [J][8] opt bytes + [J] counts
+  uint8_t* vopt_s = sm_rows + static_cast<size_t>(T) * row_p;
+  uint8_t* nval_s = vopt_s + static_cast<size_t>(J) * kSlots;
+  for (int x = threadIdx.x; x < J * kSlots; x += T) vopt_s[x] = s.vopt[x];
+  for (int x = threadIdx.x; x < J; x += T) nval_s[x] = static_cast<uint8_t>(s.nvalid[x]);
   const long long c0 = static_cast<long long>(blockIdx.x) * T;
   const long long c = c0 + threadIdx.x;
-  const int J = s.J;
   if (c < s.chains) {
     const uint64_t gid = s.chain_base + static_cast<uint64_t>(c);
     for (int x = J * PB; x < row_p; ++x) sp[x] = 0;
     for (int j = 0; j < J; ++j) prio_st<PB>(sp, j, j);
-    uint64_t x = rng_u64(s.seed, gid, 0x200000000ull) | 1ull;
+    // Fisher-Yates on a per-chain 32-bit LCG seeded by the counter-based generator: one IMAD per draw on the
+    // serial path, the bounded index from the HIGH bits (mulhi)
+    uint32_t x = static_cast<uint32_t>(rng_u64(s.seed, gid, 0x200000000ull) >> 32) | 1u;
     for (int i = J - 1; i > 0; --i) {
-      x = x * 6364136223846793005ull + 1442695040888963407ull;
-      const uint32_t u = static_cast<uint32_t>((x ^ (x >> 29)) >> 32);
-      const int k = static_cast<int>((static_cast<uint64_t>(u) * static_cast<uint32_t>(i + 1)) >> 32);
+      x = x * 1664525u + 1013904223u;
+      const int k = static_cast<int>(__umulhi(x ^ (x >> 15), static_cast<uint32_t>(i + 1)));
       const int a = prio_ld<PB>(sp, i), b = prio_ld<PB>(sp, k);
       prio_st<PB>(sp, i, b);
       prio_st<PB>(sp, k, a);
@@ -104,21 +105,37 @@ __global__ void k_init_population_smem(SearchDev s, int row_p) {
   }
   __syncthreads();
   const int wo = static_cast<int>(s.stride_o >> 2), wp = static_cast<int>(s.stride_p >> 2);  // strides are multiples of 32 B
-  for (int r = 0; r < T && c0 + r < s.chains; ++r) {
+  const uint32_t seed_lo = static_cast<uint32_t>(s.seed) ^ static_cast<uint32_t>(s.seed >> 32) * 0x9e3779b1u;
+  // write-out, all threads busy: the (row, word) pairs of the CTA are dealt round-robin
+  const int rows = static_cast<int>(min(static_cast<long long>(T), s.chains - c0));
+  for (int x = threadIdx.x; x < rows * wo; x += T) {
+    const int r = x / wo, w = x - r * wo;
     const uint8_t* rp = sm_rows + static_cast<size_t>(r) * row_p;
     const uint64_t gid = s.chain_base + static_cast<uint64_t>(c0 + r);
-    uint32_t* go = reinterpret_cast<uint32_t*>(s.cur_o + (c0 + r) * s.stride_o);
-    uint32_t* gp = reinterpret_cast<uint32_t*>(s.cur_p + (c0 + r) * s.stride_p);
-    for (int w = threadIdx.x; w < wo; w += T) {
-      uint32_t v = 0;
+    uint32_t v = 0;
+    if (w * 4 < J) {
+      const uint32_t g32 = static_cast<uint32_t>(gid) * 0x9e3779b1u ^ static_cast<uint32_t>(gid >> 32) ^ seed_lo;
+      const uint32_t h0 = hash32(g32 + 2u * w), h1 = hash32(g32 + 2u * w + 1u);
+      const uint32_t hn = s.nodes > 1 ? hash32(~g32 + w) : 0u;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = w * 4 + q;
-        if (i < J) v |= static_cast<uint32_t>(init_opt_byte(s, gid, POS ? prio_ld<PB>(rp, i) : i)) << (8 * q);
+        if (i < J) {
+          const int j = POS ? prio_ld<PB>(rp, i) : i;
+          const uint32_t f = ((q & 2) ? h1 : h0) >> (16 * (q & 1)) & 0xffffu;   // 16 random bits per byte
+          uint32_t ob = vopt_s[j * kSlots + ((f * nval_s[j]) >> 16)];
+          if (s.nodes > 1) ob = (ob & 7u) | ((((hn >> (8 * q)) & 0xffu) * static_cast<uint32_t>(s.nodes) >> 8) << 3);
+          v |= ob << (8 * q);
+        }
       }
-      go[w] = v;
     }
-    for (int w = threadIdx.x; w < wp; w += T) gp[w] = (w * 4 < row_p) ? reinterpret_cast<const uint32_t*>(rp)[w] : 0u;
+    reinterpret_cast<uint32_t*>(s.cur_o + (c0 + r) * s.stride_o)[w] = v;
+  }
+  for (int x = threadIdx.x; x < rows * wp; x += T) {
+    const int r = x / wp, w = x - r * wp;
+    const uint8_t* rp = sm_rows + static_cast<size_t>(r) * row_p;
+    reinterpret_cast<uint32_t*>(s.cur_p + (c0 + r) * s.stride_p)[w] =
+        (w * 4 < row_p) ? reinterpret_cast<const uint32_t*>(rp)[w] : 0u;
   }
 }
 
@@ -521,7 +538,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     const bool inc = win && a.sf.snap != nullptr;
     float* snap_t = inc ? a.sf.snap + static_cast<size_t>(tile) * (static_cast<size_t>(nwin - 1) * 2 * 9 * 32) : nullptr;
     uint32_t par = 0;
-    const uint32_t inc_bits = EVAL ? 0u : launch_incumbent_bits(a.sf);
+    [[maybe_unused]] const uint32_t inc_bits = EVAL ? 0u : launch_incumbent_bits(a.sf);
     const int r_end = EVAL ? 1 : a.sf.nrounds;
 #pragma unroll 1
     for (int r = inc ? -1 : 0; r < r_end; ++r) {
@@ -531,7 +548,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
       if (win && !fill) {
         const uint64_t wr = rng_u64(a.sf.seed ^ 0x31d0ull, a.sf.chain_base + static_cast<uint64_t>(a.first + tile * 32),
                                     static_cast<uint64_t>(round));
-        w0 = static_cast<int>(bounded(wr, nwin));
+        w0 = draw_window(wr, nwin, a.sf.win_bias);
       }
       PosMove mv = none;
       if (moving && !fill) {
@@ -578,7 +595,9 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
         }
       }
       if (a.best_key != nullptr) fold_best(a.best_key, active, mk, a.id_base + static_cast<uint32_t>(tile * 32 + lane), lane);
-      if (active && !EVAL && __float_as_uint(mk) < inc_bits) moving = false;  // see launch_incumbent_bits
+      if constexpr (!EVAL) {
+        if (active && __float_as_uint(mk) < inc_bits) moving = false;  // see launch_incumbent_bits
+      }
     }
   }
   if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
@@ -601,13 +620,14 @@ static int init_row(int bytes) {
 template <bool POS>
 static cudaError_t init_population_smem(const SearchDev& s, cudaStream_t st) {
   const int row_p = init_row(s.J * s.pb);
+  const size_t lists = static_cast<size_t>(s.J) * (kSlots + 1);  // staged option lists
   int threads = 128;
-  while (threads >= 32 && static_cast<size_t>(threads) * row_p > 48 * 1024) threads >>= 1;
+  while (threads >= 32 && static_cast<size_t>(threads) * row_p + lists > 48 * 1024) threads >>= 1;
   if (threads < 32) {
     threads = 32;
-    if (static_cast<size_t>(threads) * row_p > 220 * 1024) return cudaErrorNotSupported;
+    if (static_cast<size_t>(threads) * row_p + lists > 220 * 1024) return cudaErrorNotSupported;
   }
-  const size_t smem = static_cast<size_t>(threads) * row_p;
+  const size_t smem = static_cast<size_t>(threads) * row_p + lists;
   const int grid = static_cast<int>((s.chains + threads - 1) / threads);
   auto launch = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

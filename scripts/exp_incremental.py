@@ -17,7 +17,8 @@ from saturn_b200.search import run_search  # noqa: E402
 from saturn_b200.synth import synth_table  # noqa: E402
 
 MODES = [("round-1 moves, scored from position 0", 0x04000000), ("windowed moves, scored from position 0", 0x10000000),
-         ("windowed moves, incremental (shipped)", 0)]
+         ("windowed moves, incremental (shipped)", 0),
+         ("windowed moves, incremental, windows drawn with P(w) ~ w + 1 (experiment)", 0x01000000)]
 
 
 def main():
