@@ -106,6 +106,32 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
   // (a late peer costs this warp one NVLink round trip per look instead of stalling the CTA's slowest
   // warp), and only spins — bounded — after its last tile.  The publish of this round is in the tail.
   bool fold_pending = a.xp.counter != nullptr && a.xp.fold_prev && a.xp.seq > 1 && blockIdx.x == 0 && warp == 0;
+  // a look = two loads per lane (round number with acquire, then the key), ISSUED at one tile boundary and
+  // CONSUMED at the next: the NVLink round trip (~2 us) overlaps the tile's 16 us of evaluation instead of
+  // stalling this warp — every warp has the same number of tiles, so the folding warp's stalls were the
+  // kernel's tail (+4 us per step at N > 1 in the first round-2 version, profiles/r02_bench_8gpu.md)
+  unsigned long long pf_seen = 0ull, pf_key = ~0ull;
+  auto look_issue = [&]() {
+    if (lane < a.xp.x.world) {
+      const unsigned long long* slot = a.xp.x.peer[lane] + ((a.xp.seq - 1) & 1ull) * 2;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(pf_seen) : "l"(slot + 1) : "memory");
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pf_key) : "l"(slot) : "memory");  // valid iff pf_seen shows the round
+    }
+  };
+  auto fold_keys = [&](unsigned long long k) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, d);
+      k = o < k ? o : k;
+    }
+    if (lane == 0) atomicMin(a.best_key, k);
+    fold_pending = false;
+  };
+  auto look_consume = [&]() {  // non-blocking: uses the loads issued one tile ago
+    const unsigned long long want = a.xp.seq - 1;
+    const bool ok = lane >= a.xp.x.world || pf_seen >= want;
+    if (__all_sync(0xffffffffu, ok)) fold_keys(lane < a.xp.x.world ? pf_key : ~0ull);
+  };
   auto try_fold = [&](bool block) {
     const unsigned long long want = a.xp.seq - 1;
     unsigned long long k = ~0ull;
@@ -127,22 +153,19 @@ __global__ void __launch_bounds__(STREAM ? 512 : 384, 1) k_eval_tiles(const Tile
       if (block && lane == 0) *a.xp.error = 1;  // a peer never published: report, do not hang
       return;
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, d);
-      k = o < k ? o : k;
-    }
-    if (lane == 0) atomicMin(a.best_key, k);
-    fold_pending = false;
+    fold_keys(k);
   };
-  if (fold_pending) try_fold(false);
+  if (fold_pending) look_issue();
 
   uint32_t phase = 0;
   bool tab_ready = TABG;
   for (long long tile = static_cast<long long>(blockIdx.x) * nw + warp; tile < a.ntiles;
        tile += static_cast<long long>(gridDim.x) * nw) {
     const long long b0 = tile * 32;
-    if (!SEARCH && fold_pending) try_fold(false);
+    if (!SEARCH && fold_pending) {
+      look_consume();
+      if (fold_pending) look_issue();
+    }
     // the candidate of this lane: consecutive ids, or (search rounds, sf.deal = 1) one id from each of 32
     // far-apart blocks so that successive launches put different chains into one warp
     const long long cand = (SEARCH && a.sf.deal) ? lane * a.ntiles + tile : b0 + lane;
