@@ -54,26 +54,28 @@ def build_table(task_list):
     the table but never proposed unless a task has nothing else.
     """
     J = len(task_list)
-    # one pass over the Python objects collecting plain lists, the arithmetic is vectorised below
-    jj, kk, oo, rr, uu = [], [], [], [], []
-    for j, task in enumerate(task_list):
-        if len(task.strategies) == 0:
-            raise SolverError("task %r has no strategies; run the trial runner first" % getattr(task, "name", j))
-        for o, (g_count, strat) in enumerate(task.strategies.items()):
-            if not isinstance(g_count, (int, np.integer)) or g_count < 1 or g_count > NSLOT:
-                continue
-            rt = strat.runtime
-            if rt is not None and -1e-6 <= rt < 0:
-                rt = 0.0        # forecast's in-place decrements (executor.py:166-168) can undershoot by an ulp
-            if rt is None or not math.isfinite(rt) or rt < 0:
-                continue
-            jj.append(j); kk.append(int(g_count) - 1); oo.append(o); rr.append(float(rt))
-            uu.append(getattr(strat, "executor", True) is not None)
+    # one pass over the Python objects collecting plain lists (comprehensions: this loop is the host-side cost
+    # of a solve at J = 256), the filtering and the arithmetic are vectorised below
+    counts = [len(task.strategies) for task in task_list]
+    if 0 in counts:
+        j = counts.index(0)
+        raise SolverError("task %r has no strategies; run the trial runner first" % getattr(task_list[j], "name", j))
+    keys = [g for task in task_list for g in task.strategies]
+    strats = [st for task in task_list for st in task.strategies.values()]
+    rts = [st.runtime for st in strats]
+    jj_all = np.repeat(np.arange(J), counts)
+    oo_all = np.concatenate([np.arange(c) for c in counts]) if J else np.zeros(0, dtype=np.int64)
+    uu_all = np.fromiter((getattr(st, "executor", True) is not None for st in strats), dtype=bool, count=len(strats))
+    ok_key = np.fromiter((isinstance(g, (int, np.integer)) and 1 <= g <= NSLOT for g in keys), dtype=bool, count=len(keys))
+    r_all = np.array([np.nan if r is None else r for r in rts], dtype=np.float64)
+    r_all = np.where((r_all < 0) & (r_all >= -1e-6), 0.0, r_all)   # forecast's in-place decrements (executor.py:166-168) can undershoot by an ulp
+    ok = ok_key & np.isfinite(r_all) & (r_all >= 0)
+    jj, oo, rr, uu = jj_all[ok], oo_all[ok], r_all[ok], uu_all[ok]
+    kk = np.array([int(g) - 1 for g, k in zip(keys, ok) if k], dtype=np.int64)
     T = np.full((J, 1, NSLOT), np.inf, dtype=np.float32)
     optindex = np.full((J, NSLOT), -1, dtype=np.int64)
     usable = np.zeros((J, NSLOT), dtype=bool)
-    if jj:
-        jj, kk, oo, uu = np.asarray(jj), np.asarray(kk), np.asarray(oo), np.asarray(uu)
+    if len(jj):
         r64 = np.asarray(rr, dtype=np.float64)
         v = r64.astype(np.float32)                                   # smallest fp32 >= rt: the device's start + ceil(rt)
         low = v.astype(np.float64) < r64
@@ -107,23 +109,23 @@ def plan_to_arrays(n_options: Sequence[int], opt_index: Sequence[int], start: Se
     All entries are plain Python floats.
     """
     J = len(n_options)
-    sta = [[[0.0] * J for _ in range(NSLOT)] for _ in range(nodes)]
-    tga = [[[0.0] * NSLOT for _ in range(nodes)] for _ in range(J)]
+    start_a = np.asarray(start, dtype=np.float64)
+    mask_a = np.asarray(slotmask, dtype=np.int64)
+    node_a = np.zeros(J, dtype=np.int64) if node_of is None else np.asarray(node_of, dtype=np.int64)
+    occ = ((mask_a[:, None] >> np.arange(NSLOT)[None, :]) & 1).astype(bool)        # [J][8]
+    tga_a = np.zeros((J, nodes, NSLOT))
+    sta_a = np.zeros((nodes, NSLOT, J))
+    jj, gg = np.nonzero(occ)
+    tga_a[jj, node_a[jj], gg] = 1.0
+    sta_a[node_a[jj], gg, jj] = start_a[jj]
+    bna_a = np.zeros((J, nodes))
+    bna_a[np.arange(J), node_a] = 1.0
+    sta, tga, bna = sta_a.tolist(), tga_a.tolist(), bna_a.tolist()
     bss = [[0.0] * int(n_options[t]) for t in range(J)]
-    bna = [[0.0] * nodes for _ in range(J)]
     for t in range(J):
         bss[t][int(opt_index[t])] = 1.0
-        n = int(node_of[t]) if node_of is not None else 0
-        bna[t][n] = 1.0
-        m = int(slotmask[t])
-        s = float(start[t])
-        for g in range(NSLOT):
-            if (m >> g) & 1:
-                tga[t][n][g] = 1.0
-                sta[n][g][t] = s
     pos = np.asarray(position)
-    before = (pos[:, None] < pos[None, :]).astype(np.float64)
-    boa = before.tolist()
+    boa = (pos[:, None] < pos[None, :]).astype(np.float64).tolist()
     for t in range(J):
         boa[t][t] = None
     return sta, tga, bss, bna, boa
@@ -486,32 +488,23 @@ def convert_into_comprehensible(task_list, bss, boa, tga, bna, sta):
             if ctr == want:
                 task.select_strategy(strat)
                 break
-    masks = np.zeros(J, dtype=np.int64)
-    start_time_per_task = []
-    for idx in range(J):
-        row = tga[idx][int(nodes[idx])]
-        m = 0
-        first = -1
-        for g, v in enumerate(row):
-            if round(v) == 1:
-                m |= 1 << g
-                if first < 0:
-                    first = g
-        if first < 0:
-            raise SolverError("task %d occupies no GPU in tga" % idx)
-        masks[idx] = m
-        start_time_per_task.append(sta[int(nodes[idx])][first][idx])
+    # occupancy of each task on its node: round(tga[t][n][g]) == 1  (milp.py:490-497), as one array operation
+    tga_a = np.asarray(tga, dtype=np.float64).reshape(J, -1, NSLOT)
+    occ = np.rint(tga_a[np.arange(J), nodes, :]) == 1                                # [J][8]
+    if not occ.any(axis=1).all():
+        raise SolverError("task %d occupies no GPU in tga" % int(np.argmin(occ.any(axis=1))))
+    first = np.argmax(occ, axis=1)
+    masks = (occ.astype(np.int64) << np.arange(NSLOT)[None, :]).sum(axis=1)
+    start_time_per_task = [sta[int(nodes[idx])][int(first[idx])][idx] for idx in range(J)]
     task_dependency_dict = defaultdict(list)
     if J > 1:
-        before = np.zeros((J, J), dtype=bool)      # before[p][t]: round(boa[p][t]) == 1
-        for p in range(J):
-            rowb = boa[p]
-            before[p] = [False if (v is None) else (round(v) == 1) for v in rowb]
+        # before[p][t]: round(boa[p][t]) == 1; the diagonal (None in the reference, milp.py:263-270) never counts
+        b = np.array(boa, dtype=object)
+        b[np.equal(b, None)] = 0.0
+        before = np.rint(b.astype(np.float64)) == 1
         np.fill_diagonal(before, False)
         share = ((masks[:, None] & masks[None, :]) != 0) & (nodes[:, None] == nodes[None, :])
         dep = before & share                       # dep[p][t]: p must finish before t launches
-        for idx in range(J):
-            ps = np.nonzero(dep[:, idx])[0]
-            if ps.size:
-                task_dependency_dict[task_list[idx]] = [task_list[int(p)] for p in ps]
+        for idx in np.nonzero(dep.any(axis=0))[0]:
+            task_dependency_dict[task_list[int(idx)]] = [task_list[int(p)] for p in np.nonzero(dep[:, idx])[0]]
     return node_per_task, task_dependency_dict, start_time_per_task
