@@ -513,8 +513,8 @@ def main():
         from saturn_b200.synth import CONFIGS
         peak_c, _src = measured_peak()
         configs = {}
-        for name, by_pos, reduced_c in (("C3", False, False), ("C5", True, True)):
-            Jc, Sc, Gc, _sd = CONFIGS[name]
+        for name, by_pos, reduced_c in (("C3", False, False), ("C5", True, True), ("C5_full_table", False, False)):
+            Jc, Sc, Gc, _sd = CONFIGS[name.split("_")[0]]
             Tc, vc = synth_table(Jc, Sc, Gc, seed=0)
             if reduced_c:                                    # J = 1024: the search's own view, 32 KB in shared memory
                 vr = vc.any(axis=1, keepdims=True)
@@ -543,7 +543,11 @@ def main():
                              "candidates_per_s": Bc / (msc * 1e-3), "achieved_GBps": gbs, "frac": gbs / peak_c,
                              "eval_path": eng.last_eval_path(),
                              "encoding": ("opt by schedule position, min-over-strategies table (the population "
-                                          "encoding of the J > 512 search)" if by_pos else "job-indexed opt, full table")}
+                                          "encoding of the J > 512 search)" if by_pos else
+                                          "job-indexed opt, full table" if name == "C3" else
+                                          "job-indexed opt, all 8 strategies (256 KB of table): rows re-ordered on the "
+                                          "device, position-major kernel reading the table through L1 (round 1: tile "
+                                          "kernel path 4, 1.2e8)")}
             del oc, pc, outc
         # the kernel shape the north star sketches (slot times across lanes + warp shuffles), same C4 candidates
         eng.set_table(T)

@@ -79,7 +79,8 @@ typedef enum sb_status {
 #define SB_FLAG_OPT_BY_POSITION 4u /* sb_eval only: opt[b][i] is the option of the job scheduled i-th (= of job
                                     * prio[b][i]) instead of the option of job i.  Both rows are then consumed in
                                     * order and stream through registers: no shared-memory tile, full occupancy
-                                    * at any J.  Needs 32-byte aligned rows. */
+                                    * at any J.  Needs 32-byte aligned rows.  A one-node table beyond one SM's
+                                    * shared memory (C5 with all 8 strategies: 256 KB) is read through L1 / L2. */
 #define SB_FLAG_POST_KEY 8u       /* sb_eval: when the last candidate is scored, publish *best_key in this
                                      rank's peer-visible mailbox (see sb_xchg_*); the same kernel does both */
 #define SB_FLAG_FOLD_PREV 16u     /* with SB_FLAG_POST_KEY: the kernel's prologue first MINs into *best_key the keys
@@ -132,9 +133,17 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
             unsigned flags, float* makespan_out, uint64_t* best_key, uint32_t id_base);
 
 /* which kernel the last sb_eval / sb_eval_host on this handle used:
+ * 9 = job-indexed rows where the tile kernel runs short of shared memory (J >= 1024, or a table that does not
+ *     fit beside the tiles; 32-byte aligned rows, sb_eval only): the opt rows are re-ordered into schedule order
+ *     on the device (a scratch buffer of B * row_stride bytes owned by the handle, grow-only) and scored by the
+ *     position-major kernel as under 5 / 8,
+ * 8 = position-major kernel with the table in global memory, read through L1 / L2 (a one-node table beyond one
+ *     SM's shared memory), 7 = the same with the table split over the shared memory of CTA pairs (test hook:
+ *     measured, slower than 8),
  * 6 = the alternate warp-shuffle kernel (SB_FLAG_ALT_WARPSCAN),
  * 5 = position-major kernel (SB_FLAG_OPT_BY_POSITION): both rows streamed with 256-bit loads,
- * 4 = as 3 but with the runtime table read from global memory (it does not fit in shared memory),
+ * 4 = as 3 but with the runtime table read from global memory (it does not fit in shared memory; what
+ *     sb_eval_host, whose speed is PCIe's, still takes),
  * 3 = tile kernel, opt rows by TMA bulk copy + prio rows streamed with 256-bit loads (rows 32-byte
  *     aligned: the fast path), 2 = tile kernel with TMA bulk copies of both rows (16-byte aligned),
  * 1 = tile kernel with plain row loads (unaligned rows),

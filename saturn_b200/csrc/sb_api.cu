@@ -76,6 +76,8 @@ struct sb_handle {
   std::vector<float> h_tmin;
   std::vector<uint8_t> h_args;
   unsigned long long* d_scratch = nullptr;  // 4 x u64
+  uint8_t* by_pos = nullptr;  // sb_eval: opt rows re-ordered by schedule position (path 9), grow-only
+  size_t by_pos_bytes = 0;
   // staging for sb_eval_host
   cudaStream_t hs[2] = {nullptr, nullptr};
   uint8_t* st_o[2] = {nullptr, nullptr};
@@ -195,6 +197,7 @@ int sb_destroy(sb_handle* h) {
   free_staging(h);
   free_xchg(h);
   cudaFree(h->d_scratch);
+  cudaFree(h->by_pos);
   cudaFree(h->dec_buf);
   cudaFree(h->stage_T);
   for (int i = 0; i < 2; ++i)
@@ -338,15 +341,46 @@ int sb_eval(sb_handle* h, const uint8_t* opt, const void* prio, int64_t B, int64
   if (flags & SB_FLAG_OPT_BY_POSITION) {
     if (flags & (SB_FLAG_POST_KEY | SB_FLAG_FOLD_PREV))
       return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_OPT_BY_POSITION cannot be combined with the fused key exchange");
-    cudaError_t e = eval_pos_launch(h->dev, c, h->stream);
+    int path = 5;
+    cudaError_t e = eval_pos_launch(h->dev, c, h->stream, &path);
     if (e == cudaErrorNotSupported) {
       cudaGetLastError();
       return fail(SB_ERR_UNSUPPORTED, "SB_FLAG_OPT_BY_POSITION needs 32-byte aligned rows (row_stride %% 32 == 0) and a "
-                  "table that fits in shared memory (J*S*32 bytes <= %zu)", h->dev.smem_optin - 16);
+                  "multi-node table that fits in shared memory (J*32 bytes <= %zu)", h->dev.smem_optin - 16);
     }
     CK(e);
-    h->last_path = 5;
+    h->last_path = path;
     return SB_OK;
+  }
+  // Job-indexed rows where the tile kernel runs short of shared memory — a table that does not fit beside the
+  // tiles (C5 with all strategies: 256 KB, tile kernel path 4) or J >= 1024 (33 KB of opt tile per warp: 5 warps
+  // per SM): re-order the opt bytes into schedule order on the device (h->by_pos, B x row_stride bytes, grow-only)
+  // and score them with the position-major kernel.  Measured on C5, 227,328 candidates: 3.6e8 against 1.3e8
+  // candidates/s (full table), 3.9e8 against 3.3e8 (reduced table); profiles/r02_table_homes.md.
+  // Test hooks: 0x00200000 takes this route at any size, 0x00100000 never.
+  {
+    const bool hooks = (flags & (0x80000000u | 0x40000000u | 0x00100000u | SB_FLAG_POST_KEY | SB_FLAG_FOLD_PREV |
+                                 SB_FLAG_ALT_WARPSCAN)) != 0;
+    const bool aligned = row_stride % 32 == 0 && reinterpret_cast<uintptr_t>(opt) % 32 == 0 &&
+                         reinterpret_cast<uintptr_t>(prio) % 32 == 0;
+    const int home = eval_pos_home(h->dev, c.J, c.SG, c.nodes, flags);
+    if (!hooks && aligned && B > 0 && c.J <= 6144 && home >= 0 && (home != 0 || c.J >= 1024 || (flags & 0x00200000u))) {
+      const size_t need = static_cast<size_t>(B) * static_cast<size_t>(row_stride);
+      if (need > h->by_pos_bytes) {
+        if (h->by_pos) CK(cudaFree(h->by_pos));
+        h->by_pos = nullptr;
+        h->by_pos_bytes = 0;
+        CK(cudaMalloc(&h->by_pos, need));
+        h->by_pos_bytes = need;
+      }
+      CK(opt_by_position_launch(h->dev, c, h->by_pos, h->stream));
+      EvalCall cp = c;
+      cp.opt = h->by_pos;
+      int path = 5;
+      CK(eval_pos_launch(h->dev, cp, h->stream, &path));
+      h->last_path = 9;
+      return SB_OK;
+    }
   }
   if (flags & SB_FLAG_ALT_WARPSCAN) {
     if (flags & (SB_FLAG_POST_KEY | SB_FLAG_FOLD_PREV))

@@ -311,6 +311,12 @@ __global__ void k_init_population_pos(SearchDev s) {
   }
 }
 
+// k_search_pos with the table split over a CTA pair: entries per half (a multiple of 4 = 16 bytes for TMA)
+__host__ __device__ inline uint32_t pos_tab_half(int J, int SG) {
+  const uint32_t n = static_cast<uint32_t>(J) * static_cast<uint32_t>(SG);
+  return ((n + 1u) / 2u + 3u) & ~3u;
+}
+
 struct PosArgs {
   const float* tab;
   int J, SG, nodes;
@@ -407,14 +413,28 @@ __device__ __forceinline__ PosMove make_pos_move_win(const SearchFuse& sf, int r
 
 // EVAL: the scoring-only instantiation (sb_eval with SB_FLAG_OPT_BY_POSITION, population scoring after
 // initialisation / injection): the move, snapshot and acceptance code folds away at compile time.
-template <int PB, bool INT, bool MULTI, bool EVAL = false>
+// TAB: where the runtime table lives.  0 = this CTA's shared memory.  For tables beyond one SM's shared
+// memory (C5 with all 8 strategies: 256 KB) the scoring-only instantiation has two more homes:
+// 1 = left in global memory and read through L1 / L2 (the default for such tables: this kernel keeps no tile
+// in shared memory, so the launch asks for the whole array as L1);
+// 2 = split over the shared memory of a CTA PAIR (cluster of 2): each CTA loads one half with TMA and every
+// look-up is a `ld.shared::cluster` to whichever CTA owns the entry (distributed shared memory) — built and
+// measured, 3x slower than 1, kept behind a test hook (profiles/r02_table_homes.md).
+template <int PB, bool INT, bool MULTI, bool EVAL = false, int TAB = 0>
 __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
+  static_assert(TAB == 0 || (EVAL && !MULTI), "tables outside the CTA's shared memory: scoring only, one node");
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tab_bytes = static_cast<uint32_t>(a.J) * a.SG * 4u;
+  const uint32_t tab_all = static_cast<uint32_t>(a.J) * a.SG * 4u;
+  // TAB = 2: rank r of the pair keeps entries [r * half, (r + 1) * half)
+  [[maybe_unused]] const uint32_t half = pos_tab_half(a.J, a.SG);
+  [[maybe_unused]] const uint32_t rank = TAB == 2 ? cluster_ctarank() : 0u;
+  const uint32_t tab_off = TAB == 2 ? rank * half * 4u : 0u;
+  const uint32_t tab_bytes = TAB == 1 ? 0u : (TAB == 2 ? (rank == 0 ? half * 4u : tab_all - half * 4u) : tab_all);
+  const uint32_t tab_room = TAB == 1 ? 0u : (TAB == 2 ? half * 4u : tab_all);
   float* tab_s = reinterpret_cast<float*>(smem);
-  uint64_t* bar_tab = reinterpret_cast<uint64_t*>(smem + ((tab_bytes + 15u) & ~15u));
+  uint64_t* bar_tab = reinterpret_cast<uint64_t*>(smem + ((tab_room + 15u) & ~15u));
   const uint32_t node_bytes = MULTI ? static_cast<uint32_t>(a.nodes) * 1024u : 0u;
   float4* node_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bar_tab) + 16 + static_cast<size_t>(warp) * node_bytes);
   if (threadIdx.x == 0) {
@@ -422,10 +442,12 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     mbar_fence_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_tab, tab_bytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab);
-    for (uint32_t off = 0; off < tab_bytes; off += 32768u) tma_bulk_g2s(smem + off, src + off, min(32768u, tab_bytes - off), bar_tab);
+  if constexpr (TAB != 1) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar_tab, tab_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.tab) + tab_off;
+      for (uint32_t off = 0; off < tab_bytes; off += 32768u) tma_bulk_g2s(smem + off, src + off, min(32768u, tab_bytes - off), bar_tab);
+    }
   }
   LaneState<INT, MULTI> st;
   st.tab = tab_s;
@@ -433,7 +455,28 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
   st.one = a.one;
   st.orow = nullptr;
   st.ns = node_s + lane;
-  mbar_wait(bar_tab, 0);
+  if constexpr (TAB != 1) mbar_wait(bar_tab, 0);
+  // TAB = 2: both halves are in place once the pair has met; the window addresses of the two halves, the
+  // upper one biased so that (entry index * 4) can be added to either
+  [[maybe_unused]] uint32_t base_lo = 0, base_hi = 0;
+  if constexpr (TAB == 2) {
+    cluster_sync_all();
+    base_lo = cluster_map_shared(smem_u32(tab_s), 0u);
+    base_hi = cluster_map_shared(smem_u32(tab_s), 1u) - half * 4u;
+  }
+  auto lookup = [&](int j, int o) -> float {
+    if constexpr (TAB == 0) {
+      return st.lookup_rt(j, o);
+    } else if constexpr (TAB == 1) {
+      return __ldg(a.tab + static_cast<uint32_t>(j * a.SG + o));
+    } else {
+      const uint32_t idx = static_cast<uint32_t>(j * a.SG + o);
+      const uint32_t addr = (idx >= half ? base_hi : base_lo) + idx * 4u;
+      float v;
+      asm("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+      return v;
+    }
+  };
 
   const int J = a.J;
   constexpr int PCH = PB;  // prio chunks (256-bit loads) per 32 positions
@@ -501,7 +544,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
           for (int t = 0; t < 32; ++t) {
             const int j = prio_at<PB>(qp[(t * PB) / 32].w, t % (32 / PB));
             const int o = prio_at<1>(qo.w, t);
-            st.step_resolved(o, st.lookup_rt(j, o), t & 1);
+            st.step_resolved(o, lookup(j, o), t & 1);
           }
         } else {
 #pragma unroll
@@ -509,7 +552,7 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
             if (base + t < J) {
               const int j = prio_at<PB>(qp[(t * PB) / 32].w, t % (32 / PB));
               const int o = prio_at<1>(qo.w, t);
-              st.step_resolved(o, st.lookup_rt(j, o), t & 1);
+              st.step_resolved(o, lookup(j, o), t & 1);
             }
           }
         }
@@ -601,6 +644,8 @@ __global__ void __launch_bounds__(512, 1) k_search_pos(const PosArgs a) {
     }
   }
   if (a.sf.keep.counter != nullptr) keep_best_tail(a.sf);
+  // the partner may still be reading this CTA's half of the table
+  if constexpr (TAB == 2) cluster_sync_all();
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -707,9 +752,51 @@ size_t search_pos_smem(int J, int SG, int nodes, int warps) {
   return tab_bytes + 16 + static_cast<size_t>(warps) * (nodes > 1 ? nodes * 1024u : 0u);
 }
 
+// Scoring-only launches with the table outside the CTA's own shared memory (TAB = 1 / 2 of k_search_pos).
+template <int TAB>
+static cudaError_t eval_pos_far_launch(const Device& dev, const PosArgs& a, int pb, bool ints, cudaStream_t st) {
+  const int warps = 16;
+  const size_t smem = TAB == 2 ? static_cast<size_t>(pos_tab_half(a.J, a.SG)) * 4 + 16 : 16;
+  if (smem > dev.smem_optin) return cudaErrorNotSupported;
+  const long long ntiles = (a.chains + 31) / 32;
+  const long long ctas = (ntiles + warps - 1) / warps;
+  auto launch = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    if (TAB == 2) {
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(2);
+      int pairs = 0;
+      e = cudaOccupancyMaxActiveClusters(&pairs, kern, &cfg);
+      if (e != cudaSuccess) return e;
+      if (pairs < 1) return cudaErrorNotSupported;
+      const long long want = (ctas + 1) / 2;
+      cfg.gridDim = dim3(static_cast<unsigned>(2 * (want < pairs ? want : pairs)));
+    } else {
+      // nothing but an mbarrier in shared memory: leave the SM's array to L1, which caches the table
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+      if (e != cudaSuccess) return e;
+      cfg.gridDim = dim3(static_cast<unsigned>(ctas < dev.sm_count ? ctas : dev.sm_count));
+    }
+    return cudaLaunchKernelEx(&cfg, kern, a);
+  };
+  if (pb == 1) return ints ? launch(k_search_pos<1, true, false, true, TAB>) : launch(k_search_pos<1, false, false, true, TAB>);
+  return ints ? launch(k_search_pos<2, true, false, true, TAB>) : launch(k_search_pos<2, false, false, true, TAB>);
+}
+
+// tab_home: 0 = the table in every CTA's shared memory (cudaErrorNotSupported when it does not fit);
+// scoring only, one node: 2 = split over CTA pairs, 1 = global memory
 cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float* tab, int SG, unsigned flags,
                               long long first, long long count, bool eval_only, const SearchFuse& sf,
-                              cudaStream_t st) {
+                              cudaStream_t st, int tab_home) {
   if (count <= 0) return cudaSuccess;
   PosArgs a;
   a.tab = tab; a.J = s.J; a.SG = SG; a.nodes = s.nodes;
@@ -721,11 +808,15 @@ cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float
   a.eval_only = eval_only ? 1 : 0;
   a.one = 1;
   a.sf = sf;
+  const bool ints = (flags & SB_FLAG_INTEGER_STARTS) != 0;
+  const bool multi = s.nodes > 1;
+  if (tab_home != 0) {
+    if (!eval_only || multi) return cudaErrorNotSupported;
+    return tab_home == 2 ? eval_pos_far_launch<2>(dev, a, s.pb, ints, st) : eval_pos_far_launch<1>(dev, a, s.pb, ints, st);
+  }
   const int warps = 16;
   const size_t smem = search_pos_smem(s.J, SG, s.nodes, warps);
   if (smem > dev.smem_optin) return cudaErrorNotSupported;
-  const bool ints = (flags & SB_FLAG_INTEGER_STARTS) != 0;
-  const bool multi = s.nodes > 1;
   const long long ntiles = (count + 31) / 32;
   const long long ctas = (ntiles + warps - 1) / warps;
   const int grid = static_cast<int>(ctas < dev.sm_count ? ctas : dev.sm_count);
@@ -751,11 +842,29 @@ cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float
   return ints ? launch(k_search_pos<2, true, false>) : launch(k_search_pos<2, false, false>);
 }
 
-// sb_eval with SB_FLAG_OPT_BY_POSITION: score caller rows whose opt bytes are in schedule order
-cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t st) {
-  if (c.B <= 0) return cudaSuccess;
+// Where the position-major scoring kernel keeps a table of J x SG entries: 0 = every CTA's shared memory;
+// a one-node table that does not fit there: 1 = global memory, read through L1 / L2 (with no tile in shared
+// memory the SM's whole array is L1: 5.4e8 candidates/s on the 256 KB C5 table against 6.2e8 for a table in
+// shared memory, profiles/r02_table_homes.md); -1 = nowhere (multi-node table beyond shared memory).
+// Test hooks in flags: 0x00400000 forces 2 (split over CTA pairs — measured, 3x slower than 1: scattered 4-byte
+// ld.shared::cluster), 0x00800000 forces 1.
+int eval_pos_home(const Device& dev, int J, int SG, int nodes, unsigned flags) {
+  const bool pair_ok = nodes == 1 && static_cast<size_t>(pos_tab_half(J, SG)) * 4 + 16 <= dev.smem_optin;
+  if (flags & 0x00400000u) return pair_ok ? 2 : -1;
+  if (flags & 0x00800000u) return nodes == 1 ? 1 : -1;
+  if (search_pos_smem(J, SG, nodes, 16) <= dev.smem_optin) return 0;
+  return nodes == 1 ? 1 : -1;
+}
+
+// sb_eval with SB_FLAG_OPT_BY_POSITION: score caller rows whose opt bytes are in schedule order.
+// *path: 5 = table in shared memory, 7 = table split over CTA pairs, 8 = table in global memory.
+cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path) {
   if (c.stride_o % 32 != 0 || reinterpret_cast<uintptr_t>(c.opt) % 32 != 0 || reinterpret_cast<uintptr_t>(c.prio) % 32 != 0)
     return cudaErrorNotSupported;
+  const int home = eval_pos_home(dev, c.J, c.SG, c.nodes, c.flags);
+  if (home < 0) return cudaErrorNotSupported;
+  if (path) *path = home == 0 ? 5 : (home == 2 ? 7 : 8);
+  if (c.B <= 0) return cudaSuccess;
   SearchDev s;
   s.J = c.J; s.pb = c.J <= 256 ? 1 : 2; s.nodes = c.nodes;
   s.cur_o = const_cast<uint8_t*>(c.opt);  // eval_only: rows are read, never written
@@ -765,7 +874,58 @@ cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t s
   s.keys = c.best_key;
   SearchFuse sf = {};
   sf.cur_mk = c.out;
-  return search_pos_launch(dev, s, c.tab, c.SG, c.flags, 0, c.B, true, sf, st);
+  return search_pos_launch(dev, s, c.tab, c.SG, c.flags, 0, c.B, true, sf, st, home);
+}
+
+// Job-indexed opt rows -> schedule order (out[i] = opt[prio[i]]), one warp per candidate: the row is staged in
+// shared memory, each lane gathers 4 positions per store.  sb_eval uses it to send job-indexed candidates at
+// large J to the position-major kernel.
+template <int PB>
+__global__ void __launch_bounds__(256) k_opt_by_position(const uint8_t* __restrict__ opt, const uint8_t* __restrict__ prio,
+                                                         uint8_t* __restrict__ out, long long B, int J, long long stride_o,
+                                                         long long stride_p, int row_s) {
+  extern __shared__ __align__(16) uint8_t rows[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  uint8_t* row = rows + static_cast<size_t>(warp) * row_s;
+  for (long long b = static_cast<long long>(blockIdx.x) * nw + warp; b < B; b += static_cast<long long>(gridDim.x) * nw) {
+    const uint8_t* og = opt + b * stride_o;
+    const uint8_t* pg = prio + b * stride_p;
+    __syncwarp();
+    if ((reinterpret_cast<uintptr_t>(og) & 15u) == 0) {
+      for (int i = lane * 16; i < J; i += 32 * 16) *reinterpret_cast<uint4*>(row + i) = __ldg(reinterpret_cast<const uint4*>(og + i));
+    } else {
+      for (int i = lane; i < J; i += 32) row[i] = og[i];
+    }
+    __syncwarp();
+    uint8_t* dst = out + b * stride_o;
+    for (int i = lane * 4; i < J; i += 32 * 4) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (i + t < J) {
+          const int j = PB == 1 ? pg[i + t] : reinterpret_cast<const uint16_t*>(pg)[i + t];
+          w |= static_cast<uint32_t>(row[j]) << (8 * t);
+        }
+      }
+      *reinterpret_cast<uint32_t*>(dst + i) = w;
+    }
+  }
+}
+
+// rows of `out` have the stride of the opt rows (a multiple of 4 bytes)
+cudaError_t opt_by_position_launch(const Device& dev, const EvalCall& c, uint8_t* out, cudaStream_t st) {
+  if (c.B <= 0) return cudaSuccess;
+  if (c.stride_o % 16 != 0) return cudaErrorNotSupported;
+  const int row_s = (c.J + 15) & ~15;
+  const int threads = 256;
+  const size_t smem = static_cast<size_t>(threads / 32) * row_s;
+  if (smem > 48 * 1024) return cudaErrorNotSupported;
+  const long long need = (c.B + threads / 32 - 1) / (threads / 32);
+  const long long cap = static_cast<long long>(dev.sm_count) * 8;
+  const int grid = static_cast<int>(need < cap ? need : cap);
+  if (c.J <= 256) k_opt_by_position<1><<<grid, threads, smem, st>>>(c.opt, c.prio, out, c.B, c.J, c.stride_o, c.stride_p, row_s);
+  else k_opt_by_position<2><<<grid, threads, smem, st>>>(c.opt, c.prio, out, c.B, c.J, c.stride_o, c.stride_p, row_s);
+  return cudaGetLastError();
 }
 
 }  // namespace sb

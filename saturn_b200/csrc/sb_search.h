@@ -28,8 +28,10 @@ cudaError_t search_init_population_pos(const SearchDev& s, cudaStream_t st);
 size_t search_pos_smem(int J, int SG, int nodes, int warps);
 cudaError_t search_pos_launch(const Device& dev, const SearchDev& s, const float* tab, int SG, unsigned flags,
                               long long first, long long count, bool eval_only, const SearchFuse& sf,
-                              cudaStream_t st);
-cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t st);
+                              cudaStream_t st, int tab_home = 0);
+int eval_pos_home(const Device& dev, int J, int SG, int nodes, unsigned flags);
+cudaError_t eval_pos_launch(const Device& dev, const EvalCall& c, cudaStream_t st, int* path = nullptr);
+cudaError_t opt_by_position_launch(const Device& dev, const EvalCall& c, uint8_t* out, cudaStream_t st);
 cudaError_t search_resample(const SearchDev& s, int round, cudaStream_t st);
 cudaError_t search_inject(const SearchDev& s, const uint8_t* cand_o, const uint8_t* cand_p, long long first,
                           int copies, cudaStream_t st);

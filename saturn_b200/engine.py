@@ -123,10 +123,14 @@ class Engine:
     def eval(self, opt: torch.Tensor, prio: torch.Tensor, integer_starts: bool = True, reduced: bool = False,
              out: Optional[torch.Tensor] = None, best_key: Optional[torch.Tensor] = None, id_base: int = 0,
              _force_generic: bool = False, _no_stream: bool = False, post_key: bool = False, fold_prev: bool = False,
-             by_position: bool = False, _plain_addr: bool = False, alt_shape: bool = False) -> torch.Tensor:
+             by_position: bool = False, _plain_addr: bool = False, alt_shape: bool = False,
+             _table_home: int = 0, _reorder: Optional[bool] = None) -> torch.Tensor:
         """Makespan of every candidate (device tensors).  Asynchronous on the handle's stream.
         by_position: opt[b][i] is the option of the job scheduled i-th (see `opt_by_position`).
-        alt_shape: the alternate warp-shuffle kernel (SB_FLAG_ALT_WARPSCAN; a measurement, not a fast path)."""
+        alt_shape: the alternate warp-shuffle kernel (SB_FLAG_ALT_WARPSCAN; a measurement, not a fast path).
+        Test hooks: _table_home 2 / 1 puts the position-major kernel's table in a CTA pair's shared memory / in
+        global memory whatever its size; _reorder True / False forces / forbids the route that re-orders
+        job-indexed opt rows on the device (path 9)."""
         B, stride = self._check_cands(opt, prio, True)
         if out is None:
             out = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -134,7 +138,9 @@ class Engine:
             0x40000000 if _no_stream else 0) | (0x02000000 if _plain_addr else 0) | (
             _lib.FLAG_POST_KEY if post_key else 0) | (
             _lib.FLAG_FOLD_PREV if (post_key and fold_prev) else 0) | (
-            _lib.FLAG_OPT_BY_POSITION if by_position else 0) | (_lib.FLAG_ALT_WARPSCAN if alt_shape else 0)
+            _lib.FLAG_OPT_BY_POSITION if by_position else 0) | (_lib.FLAG_ALT_WARPSCAN if alt_shape else 0) | (
+            {0: 0, 1: 0x00800000, 2: 0x00400000}[_table_home]) | (
+            0 if _reorder is None else (0x00200000 if _reorder else 0x00100000))
         kp = C.c_void_p(best_key.data_ptr()) if best_key is not None else None
         check(self._lib.sb_eval(self._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), B, stride, fl,
                                 C.c_void_p(out.data_ptr()), kp, id_base & 0xffffffff))

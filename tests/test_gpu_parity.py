@@ -349,18 +349,74 @@ def test_large_batch_64bit_indexing(engine):
 
 
 def test_large_table_in_global_memory(engine):
-    """J = 1024 with the full 8-strategy table (256 KB) does not fit in shared memory: the tile kernel
-    keeps the table in global memory (path 4); results still equal the oracle and the generic kernel."""
+    """J = 1024 with the full 8-strategy table (256 KB) does not fit in one SM's shared memory.  Default route
+    (path 9): the opt rows are re-ordered into schedule order on the device and scored by the position-major
+    kernel, which reads the table through L1.  With that route switched off the tile kernel keeps the table in
+    global memory beside its tiles (path 4).  Both equal the oracle and the generic kernel."""
     J, S, G, B = 1024, 8, 8, 3000
     T, valid = R.synth_table(J, S, G, seed=5)
     engine.set_table(T)
     tab = R.canon_table(T, range(1, 9))
     opt, prio = random_candidates(engine, B, valid, seed=6)
-    a = engine.eval(opt, prio)
-    assert engine.last_eval_path() == 4
     ref = c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy().astype(np.uint16), True, np.float32, threads=8)
+    key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=engine.device)
+    a = engine.eval(opt, prio, best_key=key, id_base=7)
+    assert engine.last_eval_path() == 9
     assert np.array_equal(a.cpu().numpy(), ref)
+    i = int(np.argmin(ref))
+    assert int(key.item()) == (int(ref[i:i + 1].view(np.uint32)[0]) << 32) | (7 + i)
+    b = engine.eval(opt, prio, _reorder=False)
+    assert engine.last_eval_path() == 4
+    assert torch.equal(a, b)
     assert torch.equal(a, engine.eval(opt, prio, _force_generic=True))
+    assert np.array_equal(engine.eval(opt, prio, integer_starts=False).cpu().numpy(),
+                          c_oracle.evaluate(tab, opt.cpu().numpy(), prio.cpu().numpy().astype(np.uint16), False,
+                                            np.float32, threads=8))
+    # 512 KB of table: same route
+    T2, valid2 = R.synth_table(2048, 8, G, seed=5)
+    engine.set_table(T2)
+    o2, p2 = random_candidates(engine, 300, valid2, seed=6)
+    c = engine.eval(o2, p2)
+    assert engine.last_eval_path() == 9
+    assert np.array_equal(c.cpu().numpy(), c_oracle.evaluate(R.canon_table(T2, range(1, 9)), o2.cpu().numpy(),
+                                                             p2.cpu().numpy().astype(np.uint16), True, np.float32,
+                                                             threads=8))
+
+
+@pytest.mark.parametrize("J,S,B", [(256, 8, 3000), (64, 6, 1500), (1024, 1, 700), (33, 2, 77), (1500, 1, 200),
+                                   (520, 3, 1111), (1024, 8, 40000)])
+@pytest.mark.parametrize("ints", [True, False])
+def test_position_major_table_homes(engine, J, S, B, ints):
+    """The position-major scoring kernel with its table (a) in global memory, read through L1 / L2 (path 8: the
+    home of tables beyond one SM's shared memory), (b) split over the shared memory of a CTA pair and read with
+    ld.shared::cluster (path 7: the measured alternative), and the job-indexed route that re-orders the opt rows
+    on the device first (path 9): all bit-exact against the oracle, same arg-min key."""
+    from saturn_b200.engine import opt_by_position
+    T, valid = R.synth_table(J, S, 8, seed=J + S, masked=(S > 1 and J < 1000))
+    engine.set_table(T)
+    reduced = S == 1
+    opt, prio = random_candidates(engine, B, valid, seed=15)
+    ref = c_oracle.evaluate(R.canon_table(T, range(1, 9)), opt.cpu().numpy(), prio.cpu().numpy(), ints, np.float32,
+                            threads=8)
+    i = int(np.argmin(ref))
+    want_key = (int(ref[i:i + 1].view(np.uint32)[0]) << 32) | (1000 + i)
+    obp = opt_by_position(opt, prio)
+    for home, path in ((2, 7), (1, 8)):
+        key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=engine.device)
+        got = engine.eval(obp, prio, integer_starts=ints, reduced=reduced, by_position=True, best_key=key,
+                          id_base=1000, _table_home=home)
+        assert engine.last_eval_path() == path
+        assert np.array_equal(got.cpu().numpy(), ref)
+        assert int(key.item()) == want_key
+    key = torch.full((1,), 2 ** 63 - 1, dtype=torch.int64, device=engine.device)
+    got = engine.eval(opt, prio, integer_starts=ints, reduced=reduced, best_key=key, id_base=1000, _reorder=True)
+    assert engine.last_eval_path() == 9
+    assert np.array_equal(got.cpu().numpy(), ref)
+    assert int(key.item()) == want_key
+    if J * S * 32 + 16 > 227 * 1024:                               # the full C5 table: global memory is the default home
+        got = engine.eval(obp, prio, integer_starts=ints, by_position=True)
+        assert engine.last_eval_path() == 8
+        assert np.array_equal(got.cpu().numpy(), ref)
 
 
 def test_error_paths_and_unpadded_host_buffers(engine):
@@ -430,11 +486,11 @@ def test_opt_by_position_is_refused_where_it_cannot_run(engine):
         bad = C.c_int64(0)
         _lib.check(engine._lib.sb_validate(engine._h, C.c_void_p(opt.data_ptr()), C.c_void_p(prio.data_ptr()), 64,
                                            opt.stride(0), _lib.FLAG_OPT_BY_POSITION, C.byref(bad)))
-    T2, valid2 = R.synth_table(1024, 8, 8, seed=1)                 # 256 KB table: does not fit in shared memory
-    engine.set_table(T2)
-    o2, p2 = random_candidates(engine, 32, valid2, seed=1)
+    T2, valid2 = R.synth_table(8000, 1, 8, seed=1)                 # two nodes: 250 KB of reduced table + node states
+    engine.set_table(T2, nodes=2)
+    o2, p2 = random_candidates(engine, 32, valid2, seed=1, nodes=2)
     with pytest.raises(RuntimeError, match="shared memory"):
-        engine.eval(opt_by_position(o2, p2), p2, by_position=True)
+        engine.eval(opt_by_position(o2, p2), p2, reduced=True, by_position=True)
 
 
 def test_c5_route_parity(engine):
