@@ -223,6 +223,13 @@ def main_extra():
     (run offline, several instances side by side) -> tests/golden/milp_cases_extra.json."""
     import multiprocessing as mp
     jobs = []
+    if "--part3" in sys.argv:
+        # more J = 6 (and a few J = 5) instances of the shapes HiGHS closes: H6 at the largest size it can prove
+        for i, opts in enumerate(([8], [8], [8], [4, 8], [4, 8], [4, 8], [2, 8], [2, 8], [1, 8], [1, 8], [2, 4])):
+            jobs.append(("J6_g%s_seed%d" % ("".join(map(str, opts)), 100 + i), probe_tuples(6, opts, 100 + i), 1200))
+        for seed in range(110, 114):
+            jobs.append(("H5_hetero_seed%d" % seed, hetero_tuples(5, seed), 1200))
+        return _run_extra(jobs, "milp_cases_extra3.json", "--extra --part3")
     if "--part2" in sys.argv:
         # instances of the sizes HiGHS closes to a zero gap within minutes: more proven optima for H6
         for seed in range(50, 62):
